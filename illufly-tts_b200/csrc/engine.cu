@@ -1,0 +1,975 @@
+// The synthesis graph of illufly-tts' engine (BatchKModel.forward_batch, /root/reference/src/illufly_tts/core/kmodel.py:62-143;
+// module maths = kokoro 0.9.4, restated in SURVEY.md Appendix A) scheduled as sm_100a kernels over ragged channels-last rows.
+// No CPU arithmetic here besides the one-off weight fold/repack at load time and the segment tables.
+#include "engine.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/ttsb200.h"
+
+namespace ttsb {
+
+long long g_launches = 0;
+static thread_local char g_err[1024] = "";
+const char* last_error() { return g_err; }
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define CK(expr)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t ck_e__ = (expr);                                                                        \
+    if (ck_e__ != cudaSuccess) {                                                                        \
+      set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(ck_e__), __FILE__, __LINE__, #expr);     \
+      return TTSB_E_CUDA;                                                                               \
+    }                                                                                                   \
+  } while (0)
+#define RC(expr)                                  \
+  do {                                            \
+    int rc__ = (expr);                            \
+    if (rc__ != TTSB_OK) return rc__;             \
+  } while (0)
+
+// ======================================================================================================
+// arena
+// ======================================================================================================
+void Arena::release() {
+  for (auto& c : chunks_) cudaFree(c.p);
+  chunks_.clear();
+  total_used_ = 0;
+}
+void Arena::reset() {
+  if (chunks_.size() > 1) {
+    size_t cap = 0;
+    for (auto& c : chunks_) cap += c.cap;
+    release();
+    char* p = nullptr;
+    if (cudaMalloc(&p, cap) == cudaSuccess) chunks_.push_back({p, cap, 0});
+    else (void)cudaGetLastError();
+  }
+  for (auto& c : chunks_) c.off = 0;
+  total_used_ = 0;
+}
+void* Arena::alloc(size_t bytes) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (bytes == 0) bytes = 256;
+  if (!chunks_.empty()) {
+    Chunk& c = chunks_.back();
+    if (c.off + bytes <= c.cap) { void* r = c.p + c.off; c.off += bytes; total_used_ += bytes; return r; }
+  }
+  size_t cap = std::max(bytes, size_t(256) << 20);
+  char* p = nullptr;
+  if (cudaMalloc(&p, cap) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  chunks_.push_back({p, cap, bytes});
+  total_used_ += bytes;
+  return p;
+}
+
+// ======================================================================================================
+// weight fold / repack (host, once)
+// ======================================================================================================
+namespace {
+
+struct Loader {
+  Engine& e;
+  std::string missing;
+  explicit Loader(Engine& en) : e(en) {}
+
+  const HostTensor* get(const std::string& name, bool required = true) {
+    auto it = e.host.find(name);
+    if (it == e.host.end()) {
+      if (required && missing.empty()) missing = name;
+      return nullptr;
+    }
+    return &it->second;
+  }
+  template <typename T>
+  T* upload(const std::vector<T>& v) {
+    T* d = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    if (cudaMalloc(&d, bytes) != cudaSuccess) { if (missing.empty()) missing = "<cudaMalloc failed>"; return nullptr; }
+    e.dev_allocs.push_back(d);
+    if (!v.empty() && cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+      if (missing.empty()) missing = "<cudaMemcpy failed>";
+    }
+    return d;
+  }
+  float* upload_named(const std::string& name) {
+    const HostTensor* t = get(name);
+    if (!t) return nullptr;
+    return upload(t->data);
+  }
+  // plain or weight-normed (old style weight_g/weight_v, norm over all dims but 0) weight, as a dense host tensor
+  bool weight(const std::string& prefix, HostTensor& out) {
+    if (const HostTensor* w = get(prefix + ".weight", false)) { out = *w; return true; }
+    const HostTensor* g = get(prefix + ".weight_g");
+    const HostTensor* v = get(prefix + ".weight_v");
+    if (!g || !v) return false;
+    out.shape = v->shape;
+    out.data.resize(v->data.size());
+    const int64_t n0 = v->shape[0];
+    const int64_t inner = v->numel() / n0;
+    for (int64_t i = 0; i < n0; ++i) {
+      double ss = 0.0;
+      for (int64_t j = 0; j < inner; ++j) { const float x = v->data[i * inner + j]; ss += (double)x * (double)x; }
+      // torch: w = v * (g / norm(v)); norm is computed in fp32
+      const float nrm = (float)sqrt(ss);
+      const float sc = g->data[i] / nrm;
+      for (int64_t j = 0; j < inner; ++j) out.data[i * inner + j] = v->data[i * inner + j] * sc;
+    }
+    return true;
+  }
+  // torch Conv1d weight [Cout, Cin, k] (or Linear [Cout, Cin]) -> ConvW
+  void pack_conv(const HostTensor& w, const std::vector<float>* bias, ConvW& c, bool want_bf16);
+  bool conv(const std::string& prefix, ConvW& c, bool has_bias = true, bool want_bf16 = false) {
+    HostTensor w;
+    if (!weight(prefix, w)) return false;
+    const HostTensor* b = has_bias ? get(prefix + ".bias") : nullptr;
+    if (has_bias && !b) return false;
+    pack_conv(w, b ? &b->data : nullptr, c, want_bf16);
+    return true;
+  }
+  bool lstm(const std::string& prefix, LstmW& l);
+  bool resblk1d(const std::string& prefix, ResBlk1dW& r, int cin, int cout, bool up, std::vector<float>& style_w, std::vector<float>& style_b,
+                bool want_bf16);
+  bool resblock1(const std::string& prefix, ResBlock1W& r, int C, int k, std::vector<float>& style_w, std::vector<float>& style_b);
+  // append one AdaIN / AdaLayerNorm fc (Linear 128 -> n) to a concatenated style projection; returns its column offset
+  bool style_fc(const std::string& prefix, int n, std::vector<float>& style_w, std::vector<float>& style_b, AdainRef& ref, int C) {
+    const HostTensor* w = get(prefix + ".weight");
+    const HostTensor* b = get(prefix + ".bias");
+    if (!w || !b) return false;
+    if (w->numel() != (int64_t)n * 128 || b->numel() != n) { if (missing.empty()) missing = prefix + " (shape)"; return false; }
+    ref.off = (int)style_b.size();
+    ref.C = C;
+    style_w.insert(style_w.end(), w->data.begin(), w->data.end());   // rows = outputs, [n,128]
+    style_b.insert(style_b.end(), b->data.begin(), b->data.end());
+    while (style_b.size() & 3) { style_b.push_back(0.f); style_w.insert(style_w.end(), 128, 0.f); }
+    return true;
+  }
+};
+
+void Loader::pack_conv(const HostTensor& w, const std::vector<float>* bias, ConvW& c, bool want_bf16) {
+  const int Cout = (int)w.shape[0], Cin = (int)w.shape[1], k = w.shape.size() > 2 ? (int)w.shape[2] : 1;
+  c.Cin = Cin; c.Cout = Cout; c.k = k;
+  c.ldw = (Cout + 3) & ~3;
+  std::vector<float> p((size_t)k * Cin * c.ldw, 0.f);
+  for (int co = 0; co < Cout; ++co)
+    for (int ci = 0; ci < Cin; ++ci)
+      for (int j = 0; j < k; ++j) p[((size_t)j * Cin + ci) * c.ldw + co] = w.data[((size_t)co * Cin + ci) * k + j];
+  c.w = upload(p);
+  c.bias = bias ? upload(*bias) : nullptr;
+  if (want_bf16) {
+    std::vector<__nv_bfloat16> pb;
+    pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, pb, c.cin_pad, c.cout_pad);
+    c.wb = upload(pb);
+  }
+}
+
+bool Loader::lstm(const std::string& prefix, LstmW& l) {
+  const char* sfx[2] = {"", "_reverse"};
+  const HostTensor* wih[2]; const HostTensor* whh[2]; const HostTensor* bih[2]; const HostTensor* bhh[2];
+  for (int d = 0; d < 2; ++d) {
+    wih[d] = get(prefix + ".weight_ih_l0" + sfx[d]);
+    whh[d] = get(prefix + ".weight_hh_l0" + sfx[d]);
+    bih[d] = get(prefix + ".bias_ih_l0" + sfx[d]);
+    bhh[d] = get(prefix + ".bias_hh_l0" + sfx[d]);
+    if (!wih[d] || !whh[d] || !bih[d] || !bhh[d]) return false;
+  }
+  const int In = (int)wih[0]->shape[1];
+  HostTensor w; w.shape = {2048, In}; w.data.resize((size_t)2048 * In);
+  std::vector<float> bias(2048);
+  for (int d = 0; d < 2; ++d) {
+    memcpy(&w.data[(size_t)d * 1024 * In], wih[d]->data.data(), sizeof(float) * 1024 * In);
+    for (int g = 0; g < 1024; ++g) bias[d * 1024 + g] = bih[d]->data[g] + bhh[d]->data[g];
+  }
+  pack_conv(w, &bias, l.ih, false);
+  std::vector<float> t((size_t)2 * 256 * 1024);
+  for (int d = 0; d < 2; ++d)
+    for (int g = 0; g < 1024; ++g)
+      for (int kk = 0; kk < 256; ++kk) t[((size_t)d * 256 + kk) * 1024 + g] = whh[d]->data[(size_t)g * 256 + kk];
+  l.whhT = upload(t);
+  return true;
+}
+
+bool Loader::resblk1d(const std::string& prefix, ResBlk1dW& r, int cin, int cout, bool up, std::vector<float>& sw, std::vector<float>& sb,
+                      bool want_bf16) {
+  r.cin = cin; r.cout = cout; r.up = up; r.learned_sc = cin != cout;
+  bool ok = conv(prefix + ".conv1", r.conv1, true, want_bf16) && conv(prefix + ".conv2", r.conv2, true, want_bf16);
+  if (r.learned_sc) ok = ok && conv(prefix + ".conv1x1", r.sc, false, want_bf16);
+  ok = ok && style_fc(prefix + ".norm1.fc", 2 * cin, sw, sb, r.n1, cin) && style_fc(prefix + ".norm2.fc", 2 * cout, sw, sb, r.n2, cout);
+  if (up) {
+    HostTensor w;
+    if (!weight(prefix + ".pool", w)) return false;     // [C,1,3]
+    const HostTensor* b = get(prefix + ".pool.bias");
+    if (!b) return false;
+    r.pool_w = upload(w.data);
+    r.pool_b = upload(b->data);
+  }
+  return ok;
+}
+
+bool Loader::resblock1(const std::string& prefix, ResBlock1W& r, int C, int k, std::vector<float>& sw, std::vector<float>& sb) {
+  r.C = C; r.k = k;
+  bool ok = true;
+  for (int m = 0; m < 3 && ok; ++m) {
+    const std::string i = std::to_string(m);
+    ok = ok && conv(prefix + ".convs1." + i, r.c1[m], true, true) && conv(prefix + ".convs2." + i, r.c2[m], true, true);
+    ok = ok && style_fc(prefix + ".adain1." + i + ".fc", 2 * C, sw, sb, r.a1[m], C) && style_fc(prefix + ".adain2." + i + ".fc", 2 * C, sw, sb, r.a2[m], C);
+    r.alpha1[m] = upload_named(prefix + ".alpha1." + i);
+    r.alpha2[m] = upload_named(prefix + ".alpha2." + i);
+    ok = ok && r.alpha1[m] && r.alpha2[m];
+  }
+  return ok;
+}
+
+// ConvTranspose1d(Cin, Cout, K = 2*stride, stride, padding = stride/2) as `stride` polyphase 2-tap convolutions:
+//   Z[m, r*Cout + co] = sum_ci x[m-1, ci] W[ci, co, r + stride] + x[m, ci] W[ci, co, r]     (m = 0..L)
+//   out[t] = Z_flat[t + stride/2]   with Z_flat = Z viewed as [(L+1)*stride, Cout]
+bool pack_convT(Loader& ld, const std::string& prefix, int stride, ConvW& c) {
+  HostTensor w;
+  if (!ld.weight(prefix, w)) return false;            // [Cin, Cout, K]
+  const HostTensor* b = ld.get(prefix + ".bias");
+  if (!b) return false;
+  const int Cin = (int)w.shape[0], Cout = (int)w.shape[1], K = (int)w.shape[2];
+  if (K != 2 * stride) { if (ld.missing.empty()) ld.missing = prefix + " (kernel != 2*stride)"; return false; }
+  HostTensor p; p.shape = {(int64_t)stride * Cout, Cin, 2}; p.data.resize((size_t)stride * Cout * Cin * 2);
+  std::vector<float> bias((size_t)stride * Cout);
+  for (int r = 0; r < stride; ++r)
+    for (int co = 0; co < Cout; ++co) {
+      bias[(size_t)r * Cout + co] = b->data[co];
+      for (int ci = 0; ci < Cin; ++ci) {
+        float* dst = &p.data[(((size_t)r * Cout + co) * Cin + ci) * 2];
+        dst[0] = w.data[((size_t)ci * Cout + co) * K + r + stride];   // tap 0 reads x[m-1]
+        dst[1] = w.data[((size_t)ci * Cout + co) * K + r];            // tap 1 reads x[m]
+      }
+    }
+  ld.pack_conv(p, &bias, c, true);
+  return true;
+}
+
+}  // namespace
+
+int engine_finalize(Engine& e) {
+  if (e.finalized) return TTSB_OK;
+  Loader ld(e);
+  std::vector<float> swP, sbP, swD, sbD;   // concatenated style projections (prosody style / decoder style)
+  bool ok = true;
+  const std::string L = "bert.encoder.albert_layer_groups.0.albert_layers.0.";
+  e.emb_word = ld.upload_named("bert.embeddings.word_embeddings.weight");
+  e.emb_pos = ld.upload_named("bert.embeddings.position_embeddings.weight");
+  if (const HostTensor* t = ld.get("bert.embeddings.token_type_embeddings.weight")) {
+    std::vector<float> row0(t->data.begin(), t->data.begin() + 128);
+    e.emb_type = ld.upload(row0);
+  }
+  e.emb_ln_g = ld.upload_named("bert.embeddings.LayerNorm.weight");
+  e.emb_ln_b = ld.upload_named("bert.embeddings.LayerNorm.bias");
+  ok = ok && ld.conv("bert.encoder.embedding_hidden_mapping_in", e.map_in);
+  {  // q | k | v fused into one 768 -> 2304 projection
+    const HostTensor *wq = ld.get(L + "attention.query.weight"), *wk = ld.get(L + "attention.key.weight"), *wv = ld.get(L + "attention.value.weight");
+    const HostTensor *bq = ld.get(L + "attention.query.bias"), *bk = ld.get(L + "attention.key.bias"), *bv = ld.get(L + "attention.value.bias");
+    if (wq && wk && wv && bq && bk && bv) {
+      HostTensor w; w.shape = {2304, 768};
+      w.data = wq->data; w.data.insert(w.data.end(), wk->data.begin(), wk->data.end()); w.data.insert(w.data.end(), wv->data.begin(), wv->data.end());
+      std::vector<float> b = bq->data; b.insert(b.end(), bk->data.begin(), bk->data.end()); b.insert(b.end(), bv->data.begin(), bv->data.end());
+      ld.pack_conv(w, &b, e.qkv, false);
+    } else ok = false;
+  }
+  ok = ok && ld.conv(L + "attention.dense", e.att_dense) && ld.conv(L + "ffn", e.ffn) && ld.conv(L + "ffn_output", e.ffn_out);
+  e.att_ln_g = ld.upload_named(L + "attention.LayerNorm.weight"); e.att_ln_b = ld.upload_named(L + "attention.LayerNorm.bias");
+  e.full_ln_g = ld.upload_named(L + "full_layer_layer_norm.weight"); e.full_ln_b = ld.upload_named(L + "full_layer_layer_norm.bias");
+  ok = ok && ld.conv("bert_encoder", e.bert_enc);
+  for (int l = 0; l < 3 && ok; ++l) {
+    ok = ok && ld.lstm("predictor.text_encoder.lstms." + std::to_string(2 * l), e.de_lstm[l]);
+    ok = ok && ld.style_fc("predictor.text_encoder.lstms." + std::to_string(2 * l + 1) + ".fc", 1024, swP, sbP, e.de_aln[l], 512);
+  }
+  ok = ok && ld.lstm("predictor.lstm", e.dur_lstm) && ld.lstm("predictor.shared", e.shared_lstm) && ld.lstm("text_encoder.lstm", e.te_lstm);
+  ok = ok && ld.conv("predictor.duration_proj.linear_layer", e.dur_proj);
+  const int pc[3][2] = {{512, 512}, {512, 256}, {256, 256}};
+  for (int i = 0; i < 3 && ok; ++i) {
+    ok = ok && ld.resblk1d("predictor.F0." + std::to_string(i), e.f0_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, true);
+    ok = ok && ld.resblk1d("predictor.N." + std::to_string(i), e.n_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, true);
+  }
+  ok = ok && ld.conv("predictor.F0_proj", e.f0_proj) && ld.conv("predictor.N_proj", e.n_proj);
+  e.te_emb = ld.upload_named("text_encoder.embedding.weight");
+  for (int l = 0; l < 3 && ok; ++l) {
+    const std::string p = "text_encoder.cnn." + std::to_string(l);
+    ok = ok && ld.conv(p + ".0", e.te_cnn[l]);
+    e.te_ln_g[l] = ld.upload_named(p + ".1.gamma");
+    e.te_ln_b[l] = ld.upload_named(p + ".1.beta");
+  }
+  ok = ok && ld.resblk1d("decoder.encode", e.enc_blk, 514, 1024, false, swD, sbD, true);
+  for (int i = 0; i < 4 && ok; ++i)
+    ok = ok && ld.resblk1d("decoder.decode." + std::to_string(i), e.dec_blk[i], 1090, i == 3 ? 512 : 1024, i == 3, swD, sbD, true);
+  ok = ok && ld.conv("decoder.asr_res.0", e.asr_res);
+  {
+    HostTensor w;
+    if (ld.weight("decoder.F0_conv", w)) e.f0conv_w = ld.upload(w.data); else ok = false;
+    if (ld.weight("decoder.N_conv", w)) e.nconv_w = ld.upload(w.data); else ok = false;
+    e.f0conv_b = ld.upload_named("decoder.F0_conv.bias");
+    e.nconv_b = ld.upload_named("decoder.N_conv.bias");
+  }
+  const std::string G = "decoder.generator.";
+  e.src_lin_w = ld.upload_named(G + "m_source.l_linear.weight");
+  e.src_lin_b = ld.upload_named(G + "m_source.l_linear.bias");
+  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, true) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, true);
+  ok = ok && pack_convT(ld, G + "ups.0", 10, e.ups[0]) && pack_convT(ld, G + "ups.1", 6, e.ups[1]);
+  ok = ok && ld.resblock1(G + "noise_res.0", e.noise_res[0], 256, 7, swD, sbD) && ld.resblock1(G + "noise_res.1", e.noise_res[1], 128, 11, swD, sbD);
+  const int rk[3] = {3, 7, 11};
+  for (int i = 0; i < 6 && ok; ++i) ok = ok && ld.resblock1(G + "resblocks." + std::to_string(i), e.resblk[i], i < 3 ? 256 : 128, rk[i % 3], swD, sbD);
+  ok = ok && ld.conv(G + "conv_post", e.conv_post, true, true);
+  if (ok) {
+    HostTensor w;
+    w.shape = {(int64_t)sbP.size(), 128}; w.data = swP; ld.pack_conv(w, &sbP, e.style_pred, false);
+    w.shape = {(int64_t)sbD.size(), 128}; w.data = swD; ld.pack_conv(w, &sbD, e.style_dec, false);
+  }
+  if (!ok || !ld.missing.empty()) {
+    set_error("finalize: missing or malformed checkpoint tensor '%s'", ld.missing.empty() ? "?" : ld.missing.c_str());
+    return TTSB_E_INVALID;
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("finalize: upload failed"); return TTSB_E_CUDA; }
+  e.host.clear();
+  e.finalized = true;
+  return TTSB_OK;
+}
+
+// ======================================================================================================
+// run-time helpers
+// ======================================================================================================
+namespace {
+
+struct Run {
+  Engine& e;
+  cudaStream_t s;
+  std::vector<char> stage;        // host staging of segment tables, uploaded in one copy
+  char* d_tables = nullptr;
+  size_t tables_cap = 0;
+  double* stats_base = nullptr; size_t stats_cap = 0, stats_off = 0;
+  explicit Run(Engine& en) : e(en), s(en.stream) {}
+
+  template <typename T>
+  T* alloc(size_t n) {
+    T* p = (T*)e.arena.alloc(n * sizeof(T));
+    if (!p) set_error("workspace allocation of %zu bytes failed", n * sizeof(T));
+    return p;
+  }
+  // ---- segment tables: reserve device space first, fill host staging, upload once -----------------
+  int tables_begin(size_t cap) {
+    d_tables = (char*)e.arena.alloc(cap);
+    if (!d_tables) { set_error("workspace allocation failed (tables)"); return TTSB_E_NOMEM; }
+    tables_cap = cap;
+    stage.clear();
+    return TTSB_OK;
+  }
+  template <typename T>
+  const T* push(const std::vector<T>& v) {
+    size_t off = (stage.size() + 15) & ~size_t(15);
+    stage.resize(off + v.size() * sizeof(T));
+    if (!v.empty()) memcpy(stage.data() + off, v.data(), v.size() * sizeof(T));
+    return (const T*)(d_tables + off);
+  }
+  SegTab make_tab(const Space& in, const Space& out, int in_scale = 1, int out_scale = 1, bool want_tiles = true, int tile_rows = 128) {
+    std::vector<Seg> segs(in.n());
+    std::vector<Tile> tiles;
+    SegTab t;
+    for (int b = 0; b < in.n(); ++b) {
+      segs[b] = {in.off[b] * in_scale, in.len[b] * in_scale, out.off[b] * out_scale, out.len[b] * out_scale};
+      if (want_tiles)
+        for (int t0 = 0; t0 < segs[b].out_len; t0 += tile_rows) tiles.push_back({b, t0});
+    }
+    t.segs = push(segs); t.tiles = push(tiles);
+    t.nseg = in.n(); t.ntiles = (int)tiles.size();
+    t.max_out = out.maxlen * out_scale; t.max_in = in.maxlen * in_scale;
+    t.out_rows = out.total * out_scale; t.in_rows = in.total * in_scale;
+    return t;
+  }
+  int tables_upload() {
+    if (stage.size() > tables_cap) { set_error("internal: table staging overflow"); return TTSB_E_INVALID; }
+    if (stage.size() > e.pinned_cap) {
+      if (e.pinned) cudaFreeHost(e.pinned);
+      e.pinned_cap = std::max(stage.size() * 2, size_t(1) << 20);
+      CK(cudaMallocHost(&e.pinned, e.pinned_cap));
+    }
+    // the previous upload from this pinned buffer must have drained before it is overwritten
+    CK(cudaEventSynchronize(e.ev_sync));
+    memcpy(e.pinned, stage.data(), stage.size());
+    CK(cudaMemcpyAsync(d_tables, e.pinned, stage.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(e.ev_sync, s));
+    return TTSB_OK;
+  }
+  // ---- statistics slots (double sum, sum of squares per (utterance, channel)) ---------------------
+  int stats_begin(int nseg, size_t channels_per_seg) {
+    stats_cap = (size_t)nseg * channels_per_seg * 2;
+    stats_base = alloc<double>(stats_cap);
+    if (!stats_base) return TTSB_E_NOMEM;
+    stats_off = 0;
+    CK(cudaMemsetAsync(stats_base, 0, stats_cap * sizeof(double), s));
+    return TTSB_OK;
+  }
+  double* stats(int nseg, int C) {
+    const size_t n = (size_t)nseg * C * 2;
+    if (stats_off + n > stats_cap) { set_error("internal: statistics pool exhausted"); return nullptr; }
+    double* p = stats_base + stats_off;
+    stats_off += n;
+    return p;
+  }
+  int tap(const char* name, const float* d, int64_t rows, int64_t cols, int64_t ld) {
+    if (!e.taps_on) return TTSB_OK;
+    Tap& t = e.taps[name];
+    if (t.d) cudaFree(t.d);
+    t.d = nullptr; t.rows = rows; t.cols = cols;
+    if (rows * cols == 0) return TTSB_OK;
+    CK(cudaMalloc(&t.d, sizeof(float) * rows * cols));
+    CK(cudaMemcpy2DAsync(t.d, cols * sizeof(float), d, ld * sizeof(float), cols * sizeof(float), rows, cudaMemcpyDeviceToDevice, s));
+    return TTSB_OK;
+  }
+};
+
+// one convolution call; defaults = plain conv with bias
+struct ConvCall {
+  const ConvW* w = nullptr;
+  const float* x = nullptr; int ldx = 0;
+  float* y = nullptr; int ldy = 0;
+  const float* res = nullptr; int ldr = 0;
+  int dil = 1, pad = 0, stride = 1, in_shr = 0;
+  int pro = PRO_NONE; float slope = 0.f;
+  const double* pstats = nullptr; const float* gb = nullptr; int ld_gb = 0; AdainRef ad; const float* alpha = nullptr;
+  float out_scale = 1.f; int accumulate = 0; int act = ACT_NONE; float act_slope = 0.f;
+  double* ostats = nullptr;
+  bool tensor = false;           // eligible for the tcgen05 path when the engine runs in bf16 precision
+};
+
+int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = c.x; a.ldx = c.ldx; a.w = c.w->w; a.ldw = c.w->ldw; a.wb = c.w->wb; a.cin_pad = c.w->cin_pad; a.cout_pad = c.w->cout_pad;
+  a.bias = c.w->bias; a.y = c.y; a.ldy = c.ldy; a.res = c.res; a.ldr = c.ldr;
+  a.Cin = c.w->Cin; a.Cout = c.w->Cout; a.k = c.w->k; a.dil = c.dil; a.pad = c.pad; a.stride = c.stride; a.in_shr = c.in_shr;
+  a.pro = c.pro; a.slope = c.slope;
+  a.pstats = c.pstats; a.ld_pstats = c.ad.C;
+  a.gb = c.gb ? c.gb + c.ad.off : nullptr; a.ld_gb = c.ld_gb; a.beta_off = c.ad.C;
+  a.alpha = c.alpha;
+  a.out_scale = c.out_scale; a.accumulate = c.accumulate; a.act = c.act; a.act_slope = c.act_slope;
+  a.ostats = c.ostats; a.ld_ostats = c.w->Cout;
+  a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
+  if (c.pro >= PRO_ADAIN_LRELU && (!c.pstats || !c.gb)) { set_error("internal: AdaIN prologue without statistics"); return TTSB_E_INVALID; }
+  if (c.tensor && r.e.precision == TTSB_PRECISION_BF16 && conv_umma_supported(a)) {
+    CK(launch_conv_umma(a, r.s));
+  } else {
+    CK(launch_conv_simt(a, r.s));
+  }
+  return TTSB_OK;
+}
+
+// x W_ih -> gates, then the recurrence
+int run_bilstm(Run& r, const LstmW& l, const float* x, int ldx, float* gx, float* y, int ldy, const SegTab& t, const LstmSeg* lsegs) {
+  ConvCall c; c.w = &l.ih; c.x = x; c.ldx = ldx; c.y = gx; c.ldy = 2048;
+  RC(run_conv(r, c, t));
+  CK(launch_lstm(gx, l.whhT, l.ih.bias, y, ldy, lsegs, t.nseg, r.s));
+  return TTSB_OK;
+}
+
+// kokoro AdainResBlk1d.  x [in rows, ldx] with statistics xstats (ld = blk.cin); result -> y (ldy), statistics -> ystats.
+// `tin` : table in->in rows, `tout`: out->out rows, `tio`: in->out rows (only for upsampling blocks).
+int run_resblk1d(Run& r, const ResBlk1dW& b, const float* x, int ldx, const double* xstats, float* y, int ldy, double* ystats,
+                 const float* gb, int ld_gb, const SegTab& tin, const SegTab& tout, const SegTab& tio, bool tensor) {
+  const int nseg = tin.nseg;
+  const float rs2 = 0.70710678118654752440f;   // torch.rsqrt(torch.tensor(2.)) in fp32
+  const int out_rows = b.up ? tout.out_rows : tin.out_rows;
+  float* r1 = r.alloc<float>((size_t)out_rows * b.cout);
+  double* st1 = r.stats(nseg, b.cout);
+  if (!r1 || !st1) return TTSB_E_NOMEM;
+  const float* scp = x; int ldsc = ldx;
+  ConvCall c1; c1.w = &b.conv1; c1.pad = 1; c1.y = r1; c1.ldy = b.cout; c1.ostats = st1; c1.tensor = tensor;
+  if (!b.up) {
+    c1.x = x; c1.ldx = ldx; c1.pro = PRO_ADAIN_LRELU; c1.slope = 0.2f; c1.pstats = xstats; c1.gb = gb; c1.ld_gb = ld_gb; c1.ad = b.n1;
+    RC(run_conv(r, c1, tin));
+  } else {
+    const int ldp = (b.cin + 3) & ~3;
+    float* pool = r.alloc<float>((size_t)out_rows * ldp);
+    if (!pool) return TTSB_E_NOMEM;
+    if (ldp != b.cin) CK(cudaMemsetAsync(pool, 0, sizeof(float) * (size_t)out_rows * ldp, r.s));
+    CK(launch_pool_up2(x, ldx, pool, ldp, b.cin, b.pool_w, b.pool_b, xstats, b.n1.C, gb + b.n1.off, ld_gb, b.n1.C, 0.2f, tio.segs, nseg, tio.max_out, r.s));
+    c1.x = pool; c1.ldx = ldp;
+    RC(run_conv(r, c1, tout));
+  }
+  if (b.learned_sc) {
+    float* sc = r.alloc<float>((size_t)out_rows * b.cout);
+    if (!sc) return TTSB_E_NOMEM;
+    ConvCall cs; cs.w = &b.sc; cs.x = x; cs.ldx = ldx; cs.y = sc; cs.ldy = b.cout; cs.tensor = tensor;
+    if (b.up) { cs.in_shr = 1; RC(run_conv(r, cs, tio)); } else { RC(run_conv(r, cs, tin)); }
+    scp = sc; ldsc = b.cout;
+  } else if (b.up) {
+    set_error("internal: upsampling block without learned shortcut"); return TTSB_E_INVALID;
+  }
+  ConvCall c2; c2.w = &b.conv2; c2.x = r1; c2.ldx = b.cout; c2.pad = 1; c2.y = y; c2.ldy = ldy; c2.res = scp; c2.ldr = ldsc;
+  c2.pro = PRO_ADAIN_LRELU; c2.slope = 0.2f; c2.pstats = st1; c2.gb = gb; c2.ld_gb = ld_gb; c2.ad = b.n2;
+  c2.out_scale = rs2; c2.ostats = ystats; c2.tensor = tensor;
+  RC(run_conv(r, c2, b.up ? tout : tin));
+  return TTSB_OK;
+}
+
+// kokoro AdaINResBlock1.  x (ld C) with statistics xstats; the running value lives in `cur` (ld C; may equal x when
+// the caller allows in-place).  The last of the three iterations writes `(x + xt) * final_scale` into `out` (accumulating if asked).
+int run_resblock1(Run& r, const ResBlock1W& b, const float* x, const double* xstats, float* cur, float* xt, float* out, float final_scale,
+                  int accumulate, double* out_stats, const float* gb, int ld_gb, const SegTab& t) {
+  const int C = b.C, nseg = t.nseg;
+  const float* in = x;
+  const double* in_st = xstats;
+  for (int m = 0; m < 3; ++m) {
+    double* st_t = r.stats(nseg, C);
+    if (!st_t) return TTSB_E_NOMEM;
+    ConvCall c1; c1.w = &b.c1[m]; c1.x = in; c1.ldx = C; c1.y = xt; c1.ldy = C; c1.dil = b.dil[m]; c1.pad = (b.k * b.dil[m] - b.dil[m]) / 2;
+    c1.pro = PRO_ADAIN_SNAKE; c1.pstats = in_st; c1.gb = gb; c1.ld_gb = ld_gb; c1.ad = b.a1[m]; c1.alpha = b.alpha1[m]; c1.ostats = st_t; c1.tensor = true;
+    RC(run_conv(r, c1, t));
+    const bool last = m == 2;
+    double* st_n = last ? out_stats : r.stats(nseg, C);
+    if (!last && !st_n) return TTSB_E_NOMEM;
+    ConvCall c2; c2.w = &b.c2[m]; c2.x = xt; c2.ldx = C; c2.dil = 1; c2.pad = (b.k - 1) / 2;
+    c2.pro = PRO_ADAIN_SNAKE; c2.pstats = st_t; c2.gb = gb; c2.ld_gb = ld_gb; c2.ad = b.a2[m]; c2.alpha = b.alpha2[m];
+    c2.res = in; c2.ldr = C; c2.tensor = true;
+    if (last) { c2.y = out; c2.ldy = C; c2.out_scale = final_scale; c2.accumulate = accumulate; c2.ostats = out_stats; }
+    else { c2.y = cur; c2.ldy = C; c2.ostats = st_n; }
+    RC(run_conv(r, c2, t));
+    in = cur; in_st = st_n;
+  }
+  return TTSB_OK;
+}
+
+// kokoro Generator.forward: gen_in [sum L, 512] + f0 [sum L] + decoder-style gamma|beta rows -> audio [300 sum L]
+int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0, const float* gbD, int ld_gb, const float* noise, uint64_t seed,
+                  float* audio) {
+  Engine& e = r.e;
+  const int nseg = spL.n();
+  std::vector<int> lU0(nseg), lS0(nseg), lU1(nseg), lS1(nseg), lA(nseg);
+  for (int b = 0; b < nseg; ++b) {
+    const int L = spL.len[b];
+    lU0[b] = L + 1; lS0[b] = 10 * L; lU1[b] = 10 * L + 1; lS1[b] = 60 * L + 1; lA[b] = 300 * L;
+  }
+  Space spU0, spS0, spU1, spS1, spA;
+  spU0.build(lU0); spS0.build(lS0); spU1.build(lU1); spS1.build(lS1); spA.build(lA);
+  RC(r.tables_begin((size_t)nseg * 16 * sizeof(Seg) + (size_t)(spS1.total / 128 + 8 * nseg + 64) * 4 * sizeof(Tile) + 4096));
+  const SegTab tL_S1 = r.make_tab(spL, spS1, 1, 1, false);   // source + STFT
+  const SegTab tL_U0 = r.make_tab(spL, spU0);          // ups[0] polyphase
+  const SegTab tU0_S0 = r.make_tab(spU0, spS0, 10, 1, false); // flat polyphase rows -> stage-0 rows
+  const SegTab tS1_S0 = r.make_tab(spS1, spS0);        // noise_convs[0] (stride 6)
+  const SegTab tS0 = r.make_tab(spS0, spS0);
+  const SegTab tS0_U1 = r.make_tab(spS0, spU1);        // ups[1] polyphase
+  const SegTab tU1_S1 = r.make_tab(spU1, spS1, 6, 1, false);
+  const SegTab tS1 = r.make_tab(spS1, spS1);
+  const SegTab tS1_A = r.make_tab(spS1, spA, 1, 1, false);
+  RC(r.tables_upload());
+
+  // ---- harmonic source + STFT (W10, W11) ----
+  float* phase = r.alloc<float>((size_t)spL.total * 9);
+  float* har = r.alloc<float>((size_t)spS1.total * 24);
+  float* har_src = e.taps_on ? r.alloc<float>((size_t)spA.total) : nullptr;
+  if (!phase || !har) return TTSB_E_NOMEM;
+  CK(launch_source_stft(f0, noise, e.src_lin_w, e.src_lin_b, har_src, har, 24, phase, tL_S1.segs, nseg, spL.maxlen, seed, r.s));
+  if (har_src) RC(r.tap("har_source", har_src, spA.total, 1, 1));
+  RC(r.tap("har", har, spS1.total, 22, 24));
+
+  const float* xin = gen_in;      // stage input, ld = Cin of ups[i]
+  float* stage_out = nullptr;
+  for (int i = 0; i < 2; ++i) {
+    const int C = i == 0 ? 256 : 128;
+    const int s_up = i == 0 ? 10 : 6;
+    const Space& spS = i == 0 ? spS0 : spS1;
+    const Space& spU = i == 0 ? spU0 : spU1;
+    const SegTab& tS = i == 0 ? tS0 : tS1;
+    const size_t n = (size_t)spS.total * C;
+    // x_source = noise_res[i](noise_convs[i](har))
+    float* xs = r.alloc<float>(n);
+    float* xt = r.alloc<float>(n);
+    float* xs2 = r.alloc<float>(n);
+    double* st_xs = r.stats(nseg, C);
+    if (!xs || !xt || !xs2 || !st_xs) return TTSB_E_NOMEM;
+    ConvCall cn; cn.w = &e.noise_conv[i]; cn.x = har; cn.ldx = 24; cn.y = xs; cn.ldy = C; cn.ostats = st_xs; cn.tensor = false;
+    if (i == 0) { cn.stride = 6; cn.pad = 3; RC(run_conv(r, cn, tS1_S0)); } else { RC(run_conv(r, cn, tS1)); }
+    RC(run_resblock1(r, e.noise_res[i], xs, st_xs, xs, xt, xs2, 1.0f, 0, nullptr, gbD, ld_gb, tS));
+    // x = ups[i](leaky_relu(x, 0.1))  (+ ReflectionPad1d((1,0)) for the last stage) + x_source
+    float* up = r.alloc<float>((size_t)spU.total * s_up * C);
+    float* x0 = r.alloc<float>(n);
+    double* st_x0 = r.stats(nseg, C);
+    if (!up || !x0 || !st_x0) return TTSB_E_NOMEM;
+    ConvCall cu; cu.w = &e.ups[i]; cu.x = xin; cu.ldx = e.ups[i].Cin; cu.y = up; cu.ldy = s_up * C; cu.pad = 1; cu.pro = PRO_LRELU; cu.slope = 0.1f; cu.tensor = true;
+    RC(run_conv(r, cu, i == 0 ? tL_U0 : tS0_U1));
+    const SegTab& tUS = i == 0 ? tU0_S0 : tU1_S1;
+    CK(launch_up_add(up, C, s_up / 2, i == 1, xs2, C, x0, C, C, tUS.segs, nseg, tUS.max_out, st_x0, C, r.s));
+    // mean of the three parallel AdaINResBlock1
+    float* acc = r.alloc<float>(n);
+    float* cur = r.alloc<float>(n);
+    if (!acc || !cur) return TTSB_E_NOMEM;
+    for (int j = 0; j < 3; ++j)
+      RC(run_resblock1(r, e.resblk[3 * i + j], x0, st_x0, cur, xt, acc, 1.0f / 3.0f, j > 0, nullptr, gbD, ld_gb, tS));
+    RC(r.tap(i == 0 ? "gen_stage0" : "gen_stage1", acc, spS.total, C, C));
+    xin = acc;
+    stage_out = acc;
+  }
+  // conv_post on leaky_relu(x, 0.01), then exp / sin + iSTFT (W15, W16)
+  float* cp = r.alloc<float>((size_t)spS1.total * 24);
+  if (!cp) return TTSB_E_NOMEM;
+  CK(cudaMemsetAsync(cp, 0, sizeof(float) * (size_t)spS1.total * 24, r.s));
+  ConvCall cpc; cpc.w = &e.conv_post; cpc.x = stage_out; cpc.ldx = 128; cpc.y = cp; cpc.ldy = 24; cpc.pad = 3; cpc.pro = PRO_LRELU; cpc.slope = 0.01f; cpc.tensor = true;
+  RC(run_conv(r, cpc, tS1));
+  RC(r.tap("conv_post", cp, spS1.total, 22, 24));
+  CK(launch_istft(cp, 24, audio, tS1_A.segs, nseg, spS1.maxlen, r.s));
+  return TTSB_OK;
+}
+
+// gamma|beta rows of every AdaIN layer of one style half: gb[b, :] = style[b, :] W^T + bias
+int run_style(Run& r, const ConvW& w, const float* style, int ld_style, int nseg, float** out) {
+  float* gb = r.alloc<float>((size_t)nseg * w.ldw);
+  if (!gb) return TTSB_E_NOMEM;
+  Space one; one.build({nseg});
+  RC(r.tables_begin(4096));
+  const SegTab t = r.make_tab(one, one);
+  RC(r.tables_upload());
+  ConvCall c; c.w = &w; c.x = style; c.ldx = ld_style; c.y = gb; c.ldy = w.ldw;
+  RC(run_conv(r, c, t));
+  *out = gb;
+  return TTSB_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// begin(): token side, kmodel.py:62-119
+// ======================================================================================================
+int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, int B, const float* ref_s, const float* speeds, int padded_lstm,
+                 const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets) {
+  if (!e.finalized) { set_error("begin: engine not finalized"); return TTSB_E_STATE; }
+  if (B <= 0 || !ids || !token_offsets || !ref_s || !pred_dur || !frame_offsets) { set_error("begin: bad arguments"); return TTSB_E_INVALID; }
+  CK(cudaSetDevice(e.device));
+  e.begun = false;
+  e.arena.reset();
+  Run r(e);
+  std::vector<int> lens(B);
+  int Tmax = 0;
+  for (int b = 0; b < B; ++b) {
+    lens[b] = token_offsets[b + 1] - token_offsets[b];
+    if (lens[b] <= 0) { set_error("begin: utterance %d is empty", b); return TTSB_E_INVALID; }
+    if (lens[b] > 512) { set_error("begin: utterance %d has %d tokens (> 512)", b, lens[b]); return TTSB_E_TOO_LONG; }
+    Tmax = std::max(Tmax, lens[b]);
+  }
+  e.spT.build(lens);
+  e.B = B;
+  const int R = e.spT.total;
+  for (int i = 0; i < R; ++i)
+    if (ids[token_offsets[0] + i] < 0 || ids[token_offsets[0] + i] >= 178) { set_error("begin: token id out of range at %d", i); return TTSB_E_INVALID; }
+
+  // ---- tables + inputs, one upload ----
+  RC(r.tables_begin((size_t)B * (sizeof(Seg) + 2 * sizeof(LstmSeg) + 260 * sizeof(float)) + (size_t)(R / 128 + B + 8) * sizeof(Tile) + (size_t)R * 16 + 8192));
+  e.tabT = r.make_tab(e.spT, e.spT);
+  std::vector<int> h_ids(ids + token_offsets[0], ids + token_offsets[0] + R), h_pos(R), h_r2s(R);
+  std::vector<LstmSeg> ls(B), lsq(B);
+  std::vector<float> h_speed(B), h_ref(ref_s, ref_s + (size_t)B * 256);
+  for (int b = 0; b < B; ++b) {
+    for (int t = 0; t < lens[b]; ++t) { h_pos[e.spT.off[b] + t] = t; h_r2s[e.spT.off[b] + t] = b; }
+    ls[b] = {e.spT.off[b], lens[b], 0};
+    lsq[b] = {e.spT.off[b], lens[b], padded_lstm ? Tmax - lens[b] : 0};
+    h_speed[b] = speeds ? speeds[b] : 1.0f;
+  }
+  const int* d_ids = r.push(h_ids);
+  const int* d_pos = r.push(h_pos);
+  const int* d_r2s = r.push(h_r2s);
+  const LstmSeg* d_ls = r.push(ls);
+  const LstmSeg* d_lsq = r.push(lsq);
+  const float* d_speed = r.push(h_speed);
+  const float* d_ref = r.push(h_ref);
+  std::vector<int> h_forced;
+  const int* d_forced = nullptr;
+  if (forced_dur) { h_forced.assign(forced_dur, forced_dur + R); d_forced = r.push(h_forced); }
+  RC(r.tables_upload());
+  e.d_refs = const_cast<float*>(d_ref);
+  e.d_row2segT = const_cast<int*>(d_r2s);
+  const SegTab& tT = e.tabT;
+
+  // ---- style projections of the prosody half (AdaLayerNorm + F0/N AdaIN) ----
+  RC(run_style(r, e.style_pred, d_ref + 128, 256, B, &e.d_gbP));
+  const int ldP = e.style_pred.ldw;
+
+  // ---- ALBERT (A.1) ----
+  float* E = r.alloc<float>((size_t)R * 128);
+  float* H = r.alloc<float>((size_t)R * 768);
+  float* QKV = r.alloc<float>((size_t)R * 2304);
+  float* CTX = r.alloc<float>((size_t)R * 768);
+  float* A1 = r.alloc<float>((size_t)R * 768);
+  float* TMP = r.alloc<float>((size_t)R * 768);
+  float* FF = r.alloc<float>((size_t)R * 2048);
+  if (!E || !H || !QKV || !CTX || !A1 || !TMP || !FF) return TTSB_E_NOMEM;
+  CK(launch_albert_embed(d_ids, d_pos, e.emb_word, e.emb_pos, e.emb_type, e.emb_ln_g, e.emb_ln_b, E, R, r.s));
+  { ConvCall c; c.w = &e.map_in; c.x = E; c.ldx = 128; c.y = H; c.ldy = 768; RC(run_conv(r, c, tT)); }
+  for (int layer = 0; layer < 12; ++layer) {
+    { ConvCall c; c.w = &e.qkv; c.x = H; c.ldx = 768; c.y = QKV; c.ldy = 2304; RC(run_conv(r, c, tT)); }
+    CK(launch_attention(QKV, CTX, tT.segs, B, e.spT.maxlen, 12, r.s));
+    { ConvCall c; c.w = &e.att_dense; c.x = CTX; c.ldx = 768; c.y = TMP; c.ldy = 768; c.res = H; c.ldr = 768; RC(run_conv(r, c, tT)); }
+    CK(launch_layernorm(TMP, 768, nullptr, 0, A1, 768, R, 768, 1e-12f, 0, e.att_ln_g, e.att_ln_b, nullptr, 0, nullptr, ACT_NONE, 0.f, r.s));
+    { ConvCall c; c.w = &e.ffn; c.x = A1; c.ldx = 768; c.y = FF; c.ldy = 2048; c.act = ACT_GELU_NEW; RC(run_conv(r, c, tT)); }
+    { ConvCall c; c.w = &e.ffn_out; c.x = FF; c.ldx = 2048; c.y = TMP; c.ldy = 768; c.res = A1; c.ldr = 768; RC(run_conv(r, c, tT)); }
+    CK(launch_layernorm(TMP, 768, nullptr, 0, H, 768, R, 768, 1e-12f, 0, e.full_ln_g, e.full_ln_b, nullptr, 0, nullptr, ACT_NONE, 0.f, r.s));
+  }
+  RC(r.tap("bert", H, R, 768, 768));
+
+  // ---- bert_encoder + DurationEncoder (A.2, A.3) ----
+  float* X = r.alloc<float>((size_t)R * 640);
+  float* GX = r.alloc<float>((size_t)R * 2048);
+  float* Y = r.alloc<float>((size_t)R * 512);
+  if (!X || !GX || !Y) return TTSB_E_NOMEM;
+  { ConvCall c; c.w = &e.bert_enc; c.x = H; c.ldx = 768; c.y = X; c.ldy = 640; RC(run_conv(r, c, tT)); }
+  CK(launch_fill_style(d_ref, 256, 128, d_r2s, X, 640, 512, 128, R, r.s));
+  RC(r.tap("d_en", X, R, 512, 640));
+  for (int l = 0; l < 3; ++l) {
+    RC(run_bilstm(r, e.de_lstm[l], X, 640, GX, Y, 512, tT, d_ls));
+    CK(launch_layernorm(Y, 512, nullptr, 0, X, 640, R, 512, 1e-5f, 1, nullptr, nullptr, e.d_gbP + e.de_aln[l].off, ldP, d_r2s, ACT_NONE, 0.f, r.s));
+  }
+  RC(r.tap("d", X, R, 640, 640));
+  e.d_X = X;
+
+  // ---- duration head (A.4) ----
+  float* logits = r.alloc<float>((size_t)R * 52);
+  float* d_dur = r.alloc<float>(R);
+  int* d_pd = r.alloc<int>(R);
+  int* d_cum = r.alloc<int>(R);
+  int* d_tot = r.alloc<int>(B);
+  if (!logits || !d_dur || !d_pd || !d_cum || !d_tot) return TTSB_E_NOMEM;
+  RC(run_bilstm(r, e.dur_lstm, X, 640, GX, Y, 512, tT, d_lsq));
+  { ConvCall c; c.w = &e.dur_proj; c.x = Y; c.ldx = 512; c.y = logits; c.ldy = 52; RC(run_conv(r, c, tT)); }
+  CK(launch_duration(logits, 52, 50, d_r2s, d_speed, d_dur, d_pd, R, r.s));
+  const int* d_used = d_forced ? d_forced : d_pd;
+  CK(launch_dur_scan(d_used, tT.segs, B, d_cum, d_tot, r.s));
+  // results the host needs to size the frame side
+  std::vector<int> h_tot(B);
+  CK(cudaMemcpyAsync(pred_dur, d_pd, sizeof(int) * R, cudaMemcpyDeviceToHost, r.s));
+  if (duration) CK(cudaMemcpyAsync(duration, d_dur, sizeof(float) * R, cudaMemcpyDeviceToHost, r.s));
+  CK(cudaMemcpyAsync(h_tot.data(), d_tot, sizeof(int) * B, cudaMemcpyDeviceToHost, r.s));
+  CK(cudaEventRecord(e.ev0, r.s));
+  e.d_pred_dur = d_pd; e.d_cum = d_cum;
+
+  // ---- text_encoder (A.9) — queued behind the copies so it overlaps the host wait ----
+  float* TE0 = r.alloc<float>((size_t)R * 512);
+  float* TE1 = r.alloc<float>((size_t)R * 512);
+  float* TEN = r.alloc<float>((size_t)R * 512);
+  if (!TE0 || !TE1 || !TEN) return TTSB_E_NOMEM;
+  CK(launch_embedding(d_ids, e.te_emb, 512, TE0, 512, R, r.s));
+  for (int l = 0; l < 3; ++l) {
+    ConvCall c; c.w = &e.te_cnn[l]; c.x = TE0; c.ldx = 512; c.y = TE1; c.ldy = 512; c.pad = 2;
+    RC(run_conv(r, c, tT));
+    CK(launch_layernorm(TE1, 512, nullptr, 0, TE0, 512, R, 512, 1e-5f, 0, e.te_ln_g[l], e.te_ln_b[l], nullptr, 0, nullptr, ACT_LRELU, 0.2f, r.s));
+  }
+  RC(run_bilstm(r, e.te_lstm, TE0, 512, GX, TEN, 512, tT, d_ls));
+  RC(r.tap("t_en", TEN, R, 512, 512));
+  e.d_ten = TEN;
+
+  CK(cudaEventSynchronize(e.ev0));
+  std::vector<int> fl(B);
+  frame_offsets[0] = 0;
+  for (int b = 0; b < B; ++b) { fl[b] = h_tot[b]; frame_offsets[b + 1] = frame_offsets[b] + h_tot[b]; }
+  e.spF.build(fl);
+  e.begun = true;
+  return TTSB_OK;
+}
+
+// ======================================================================================================
+// finish(): frame side, kmodel.py:120-143
+// ======================================================================================================
+int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, int32_t* indices, float* audio, int audio_mem) {
+  if (!e.begun) { set_error("finish: no synthesis in flight (call begin first)"); return TTSB_E_STATE; }
+  if (!audio) { set_error("finish: audio is NULL"); return TTSB_E_INVALID; }
+  CK(cudaSetDevice(e.device));
+  e.begun = false;
+  Run r(e);
+  const int B = e.B;
+  const Space& spT = e.spT;
+  const Space& spF = e.spF;
+  const int RF = spF.total;
+  std::vector<int> lL(B);
+  for (int b = 0; b < B; ++b) lL[b] = 2 * spF.len[b];
+  Space spL; spL.build(lL);
+  const int RL = spL.total;
+
+  RC(r.tables_begin((size_t)B * 8 * sizeof(Seg) + (size_t)(RL / 128 + 4 * B + 16) * 4 * sizeof(Tile) + (size_t)RF * 4 + (size_t)B * sizeof(LstmSeg) + 8192));
+  const SegTab tTF = r.make_tab(spT, spF, 1, 1, false);
+  const SegTab tF = r.make_tab(spF, spF);
+  const SegTab tL = r.make_tab(spL, spL);
+  const SegTab tFL = r.make_tab(spF, spL);
+  const SegTab tLF = r.make_tab(spL, spF, 1, 1, false);
+  std::vector<int> f2s(RF);
+  std::vector<LstmSeg> lsF(B);
+  for (int b = 0; b < B; ++b) {
+    for (int f = 0; f < spF.len[b]; ++f) f2s[spF.off[b] + f] = b;
+    lsF[b] = {spF.off[b], spF.len[b], 0};
+  }
+  const int* d_f2s = r.push(f2s);
+  const LstmSeg* d_lsF = r.push(lsF);
+  RC(r.tables_upload());
+  RC(r.stats_begin(B, 40960));
+
+  // noise for SineGen
+  const float* d_noise = nullptr;
+  if (noise) {
+    if (noise_mem == TTSB_MEM_DEVICE) d_noise = noise;
+    else {
+      float* dn = r.alloc<float>((size_t)RF * 600 * 9);
+      if (!dn) return TTSB_E_NOMEM;
+      CK(cudaMemcpyAsync(dn, noise, sizeof(float) * (size_t)RF * 600 * 9, cudaMemcpyHostToDevice, r.s));
+      d_noise = dn;
+    }
+  }
+
+  // ---- alignment index map + length regulation (A.5) ----
+  int* d_idx = r.alloc<int>(RF);
+  float* EN = r.alloc<float>((size_t)RF * 640);
+  float* CAT0 = r.alloc<float>((size_t)RF * 516);
+  if (!d_idx || !EN || !CAT0) return TTSB_E_NOMEM;
+  CK(launch_indices(e.d_cum, tTF.segs, B, d_idx, RF, d_f2s, r.s));
+  if (indices) CK(cudaMemcpyAsync(indices, d_idx, sizeof(int) * RF, cudaMemcpyDeviceToHost, r.s));
+  CK(launch_gather_rows(e.d_X, 640, d_idx, d_f2s, tTF.segs, EN, 640, 640, RF, r.s));
+  CK(cudaMemsetAsync(CAT0, 0, sizeof(float) * (size_t)RF * 516, r.s));
+  CK(launch_gather_rows(e.d_ten, 512, d_idx, d_f2s, tTF.segs, CAT0, 516, 512, RF, r.s));
+  RC(r.tap("en", EN, RF, 640, 640));
+  RC(r.tap("asr", CAT0, RF, 512, 516));
+
+  // ---- F0Ntrain (A.6) ----
+  const float* gbP = e.d_gbP; const int ldP = e.style_pred.ldw;
+  float* GX = r.alloc<float>((size_t)RF * 2048);
+  float* SH = r.alloc<float>((size_t)RF * 512);
+  double* st_sh = r.stats(B, 512);
+  float* F0 = r.alloc<float>(RL);
+  float* NN = r.alloc<float>(RL);
+  if (!GX || !SH || !st_sh || !F0 || !NN) return TTSB_E_NOMEM;
+  RC(run_bilstm(r, e.shared_lstm, EN, 640, GX, SH, 512, tF, d_lsF));
+  CK(launch_colstats(SH, 512, 512, tF.segs, B, st_sh, 512, r.s));
+  for (int br = 0; br < 2; ++br) {
+    const ResBlk1dW* blk = br == 0 ? e.f0_blk : e.n_blk;
+    float* o0 = r.alloc<float>((size_t)RF * 512);
+    float* o1 = r.alloc<float>((size_t)RL * 256);
+    float* o2 = r.alloc<float>((size_t)RL * 256);
+    double* s0 = r.stats(B, 512); double* s1 = r.stats(B, 256);
+    if (!o0 || !o1 || !o2 || !s0 || !s1) return TTSB_E_NOMEM;
+    RC(run_resblk1d(r, blk[0], SH, 512, st_sh, o0, 512, s0, gbP, ldP, tF, tF, tF, true));
+    RC(run_resblk1d(r, blk[1], o0, 512, s0, o1, 256, s1, gbP, ldP, tF, tL, tFL, true));
+    RC(run_resblk1d(r, blk[2], o1, 256, s1, o2, 256, nullptr, gbP, ldP, tL, tL, tL, true));
+    ConvCall c; c.w = br == 0 ? &e.f0_proj : &e.n_proj; c.x = o2; c.ldx = 256; c.y = br == 0 ? F0 : NN; c.ldy = 1;
+    RC(run_conv(r, c, tL));
+  }
+  RC(r.tap("F0", F0, RL, 1, 1));
+  RC(r.tap("N", NN, RL, 1, 1));
+
+  // ---- decoder (A.10) ----
+  float* gbD = nullptr;
+  RC(run_style(r, e.style_dec, e.d_refs, 256, B, &gbD));
+  const int ldD = e.style_dec.ldw;
+  CK(launch_conv1_s2(F0, CAT0 + 512, 516, e.f0conv_w, e.f0conv_b, tLF.segs, B, spF.maxlen, nullptr, 0, r.s));
+  CK(launch_conv1_s2(NN, CAT0 + 513, 516, e.nconv_w, e.nconv_b, tLF.segs, B, spF.maxlen, nullptr, 0, r.s));
+  double* st_cat0 = r.stats(B, 514);
+  float* XDa = r.alloc<float>((size_t)RF * 1092);
+  float* XDb = r.alloc<float>((size_t)RF * 1092);
+  double* st_a = r.stats(B, 1090); double* st_b = r.stats(B, 1090);
+  float* GIN = r.alloc<float>((size_t)RL * 512);
+  if (!st_cat0 || !XDa || !XDb || !st_a || !st_b || !GIN) return TTSB_E_NOMEM;
+  CK(launch_colstats(CAT0, 516, 514, tF.segs, B, st_cat0, 514, r.s));
+  CK(cudaMemsetAsync(XDa, 0, sizeof(float) * (size_t)RF * 1092, r.s));
+  CK(cudaMemsetAsync(XDb, 0, sizeof(float) * (size_t)RF * 1092, r.s));
+  // tail columns [asr_res(64) | F0 | N] are the same for every decode block: write them into both ping-pong buffers
+  for (float* xd : {XDa, XDb}) {
+    ConvCall c; c.w = &e.asr_res; c.x = CAT0; c.ldx = 516; c.y = xd + 1024; c.ldy = 1092; c.tensor = true;
+    RC(run_conv(r, c, tF));
+    CK(launch_copy_cols(CAT0 + 512, 516, xd + 1088, 1092, 2, RF, r.s));
+  }
+  // statistics rows are [B][1090][2]: per-utterance tail statistics via one strided column-statistics pass per buffer
+  CK(launch_colstats(XDa + 1024, 1092, 66, tF.segs, B, st_a + 1024 * 2, 1090, r.s));
+  CK(launch_colstats(XDb + 1024, 1092, 66, tF.segs, B, st_b + 1024 * 2, 1090, r.s));
+  // the conv epilogue accumulates [B][Cout=1024][2]; the AdaIN prologue of the next block reads [B][1090][2]: give the
+  // producer a dense scratch and scatter it (tiny copies) — done by colstats-free strided memcpy below
+  double* st_tmp = r.stats(B, 1024);
+  if (!st_tmp) return TTSB_E_NOMEM;
+  auto scatter_stats = [&](double* dst) -> int {
+    CK(cudaMemcpy2DAsync(dst, sizeof(double) * 1090 * 2, st_tmp, sizeof(double) * 1024 * 2, sizeof(double) * 1024 * 2, B, cudaMemcpyDeviceToDevice, r.s));
+    CK(cudaMemsetAsync(st_tmp, 0, sizeof(double) * (size_t)B * 1024 * 2, r.s));
+    return TTSB_OK;
+  };
+  RC(run_resblk1d(r, e.enc_blk, CAT0, 516, st_cat0, XDa, 1092, st_tmp, gbD, ldD, tF, tF, tF, true));
+  RC(scatter_stats(st_a));
+  float* cur = XDa; double* cur_st = st_a; float* nxt = XDb; double* nxt_st = st_b;
+  for (int i = 0; i < 3; ++i) {
+    RC(run_resblk1d(r, e.dec_blk[i], cur, 1092, cur_st, nxt, 1092, st_tmp, gbD, ldD, tF, tF, tF, true));
+    RC(scatter_stats(nxt_st));
+    std::swap(cur, nxt); std::swap(cur_st, nxt_st);
+  }
+  RC(run_resblk1d(r, e.dec_blk[3], cur, 1092, cur_st, GIN, 512, nullptr, gbD, ldD, tF, tL, tFL, true));
+  RC(r.tap("gen_in", GIN, RL, 512, 512));
+
+  // ---- generator (A.11) ----
+  float* d_audio = audio;
+  if (audio_mem != TTSB_MEM_DEVICE) {
+    d_audio = r.alloc<float>((size_t)RF * 600);
+    if (!d_audio) return TTSB_E_NOMEM;
+  }
+  RC(run_generator(r, spL, GIN, F0, gbD, ldD, d_noise, seed, d_audio));
+  if (audio_mem != TTSB_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * (size_t)RF * 600, cudaMemcpyDeviceToHost, r.s));
+    CK(cudaStreamSynchronize(r.s));
+  } else if (indices || e.taps_on) {
+    CK(cudaStreamSynchronize(r.s));
+  }
+  return TTSB_OK;
+}
+
+// ======================================================================================================
+// vocoder only (BASELINE config 4)
+// ======================================================================================================
+int engine_vocoder(Engine& e, const float* x, const float* f0, const float* style, const int32_t* l_offsets, int B, int in_mem, const float* noise,
+                   uint64_t seed, float* audio, int audio_mem) {
+  if (!e.finalized) { set_error("vocoder: engine not finalized"); return TTSB_E_STATE; }
+  if (B <= 0 || !x || !f0 || !style || !l_offsets || !audio) { set_error("vocoder: bad arguments"); return TTSB_E_INVALID; }
+  CK(cudaSetDevice(e.device));
+  e.begun = false;
+  e.arena.reset();
+  Run r(e);
+  std::vector<int> lL(B);
+  for (int b = 0; b < B; ++b) {
+    lL[b] = l_offsets[b + 1] - l_offsets[b];
+    if (lL[b] <= 0) { set_error("vocoder: utterance %d is empty", b); return TTSB_E_INVALID; }
+  }
+  Space spL; spL.build(lL);
+  const size_t RL = spL.total;
+  const float *dx = x, *df0 = f0, *dstyle = style, *dnoise = noise;
+  if (in_mem != TTSB_MEM_DEVICE) {
+    float* a = r.alloc<float>(RL * 512); float* b = r.alloc<float>(RL); float* c = r.alloc<float>((size_t)B * 128);
+    if (!a || !b || !c) return TTSB_E_NOMEM;
+    CK(cudaMemcpyAsync(a, x, sizeof(float) * RL * 512, cudaMemcpyHostToDevice, r.s));
+    CK(cudaMemcpyAsync(b, f0, sizeof(float) * RL, cudaMemcpyHostToDevice, r.s));
+    CK(cudaMemcpyAsync(c, style, sizeof(float) * (size_t)B * 128, cudaMemcpyHostToDevice, r.s));
+    dx = a; df0 = b; dstyle = c;
+    if (noise) {
+      float* d = r.alloc<float>(RL * 300 * 9);
+      if (!d) return TTSB_E_NOMEM;
+      CK(cudaMemcpyAsync(d, noise, sizeof(float) * RL * 300 * 9, cudaMemcpyHostToDevice, r.s));
+      dnoise = d;
+    }
+  }
+  float* gbD = nullptr;
+  RC(run_style(r, e.style_dec, dstyle, 128, B, &gbD));
+  RC(r.stats_begin(B, 16384));
+  float* d_audio = audio;
+  if (audio_mem != TTSB_MEM_DEVICE) {
+    d_audio = r.alloc<float>(RL * 300);
+    if (!d_audio) return TTSB_E_NOMEM;
+  }
+  RC(run_generator(r, spL, dx, df0, gbD, e.style_dec.ldw, dnoise, seed, d_audio));
+  if (audio_mem != TTSB_MEM_DEVICE) {
+    CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * RL * 300, cudaMemcpyDeviceToHost, r.s));
+    CK(cudaStreamSynchronize(r.s));
+  }
+  return TTSB_OK;
+}
+
+}  // namespace ttsb

@@ -1,0 +1,373 @@
+// Text-side kernels: ALBERT embedding + LayerNorms, attention, BiLSTM recurrence, duration head,
+// duration scan / alignment index map / length-regulation gather.  All fp32: this side decides the integer
+// durations, which must match the reference bit-for-bit.
+#include "common.cuh"
+
+namespace ttsb {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm family: one warp per row, row held in registers (C <= 32*MAXV), two-pass variance.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MAXV = 24;  // 768 / 32
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ res, int ldr,
+                                                        float* __restrict__ out, int ldo, int rows, int C, float eps, int mode,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const float* __restrict__ gb, int ld_gb, const int* __restrict__ row2seg,
+                                                        int act, float slope) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    float t = 0.f;
+    if (c < C) {
+      t = x[(size_t)row * ldx + c];
+      if (res) t += res[(size_t)row * ldr + c];
+    }
+    v[i] = t;
+    s += t;
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) { const float d = v[i] - mean; q += d * d; }
+  }
+  const float var = warp_sum(q) / (float)C;
+  const float rstd = 1.0f / sqrtf(var + eps);
+  const int seg = (mode == 1) ? row2seg[row] : 0;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < C) {
+      float y = (v[i] - mean) * rstd;
+      if (mode == 1) {
+        y = (1.0f + gb[(size_t)seg * ld_gb + c]) * y + gb[(size_t)seg * ld_gb + C + c];
+      } else {
+        if (gamma) y = y * gamma[c] + beta[c];
+      }
+      if (act == ACT_LRELU) y = lrelu(y, slope);
+      out[(size_t)row * ldo + c] = y;
+    }
+  }
+}
+
+// ALBERT embeddings: LN_128(word[id] + type[0] + pos[t]), eps 1e-12 (transformers AlbertEmbeddings order: word + type, then + pos)
+__global__ void __launch_bounds__(256) albert_embed_kernel(const int* __restrict__ ids, const int* __restrict__ pos, const float* __restrict__ word,
+                                                           const float* __restrict__ posw, const float* __restrict__ type0,
+                                                           const float* __restrict__ g, const float* __restrict__ b, float* __restrict__ out, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int id = ids[row], ps = pos[row];
+  float v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + i * 32;
+    v[i] = (word[id * 128 + c] + type0[c]) + posw[ps * 128 + c];
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / 128.f;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / 128.f + 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + i * 32;
+    out[(size_t)row * 128 + c] = (v[i] - mean) * rstd * g[c] + b[c];
+  }
+}
+
+__global__ void embedding_kernel(const int* __restrict__ ids, const float* __restrict__ table, int C, float* __restrict__ out, int ldo, int rows) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const int id = ids[row];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)row * ldo + c] = table[(size_t)id * C + c];
+}
+
+__global__ void fill_style_kernel(const float* __restrict__ style, int ld_style, int style_off, const int* __restrict__ row2seg,
+                                  float* __restrict__ out, int ldo, int col_off, int C, int rows) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const int seg = row2seg[row];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) out[(size_t)row * ldo + col_off + c] = style[(size_t)seg * ld_style + style_off + c];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ALBERT self-attention: qkv rows [.., 3*H*64] (q | k | v), one warp per (query row, head).
+// scores/softmax exactly two-pass (max, exp, sum) like torch.softmax; 1/sqrt(64) applied to the scores.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int ATT_MAXK = 16;  // keys per lane: T <= 512
+
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, const Seg* __restrict__ segs, int heads) {
+  const Seg seg = segs[blockIdx.z];
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= seg.in_len) return;
+  const int H = heads * 64;
+  const int ld = 3 * H;
+  const float* qrow = qkv + (size_t)(seg.in_off + qi) * ld + head * 64;
+  float q[64];
+#pragma unroll
+  for (int d = 0; d < 64; d += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(qrow + d);
+    q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
+  }
+  float sc[ATT_MAXK];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < ATT_MAXK; ++i) {
+    const int kj = lane + i * 32;
+    float s = -INFINITY;
+    if (kj < seg.in_len) {
+      const float* krow = qkv + (size_t)(seg.in_off + kj) * ld + H + head * 64;
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < 64; d += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(krow + d);
+        a = fmaf(q[d], t.x, a); a = fmaf(q[d + 1], t.y, a); a = fmaf(q[d + 2], t.z, a); a = fmaf(q[d + 3], t.w, a);
+      }
+      s = a * 0.125f;
+    }
+    sc[i] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < ATT_MAXK; ++i) {
+    const int kj = lane + i * 32;
+    const float e = (kj < seg.in_len) ? expf(sc[i] - mx) : 0.f;
+    sc[i] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  // out[d] = sum_k p[k] v[k][d]; lane owns dims lane and lane+32
+  float o0 = 0.f, o1 = 0.f;
+  const int nk = seg.in_len;
+#pragma unroll
+  for (int i = 0; i < ATT_MAXK; ++i) {
+    const int base = i * 32;
+    if (base >= nk) break;
+    const float pi = sc[i] * inv;
+    const int lim = min(32, nk - base);
+    for (int l = 0; l < lim; ++l) {
+      const float pk = __shfl_sync(0xffffffffu, pi, l);
+      const float* vrow = qkv + (size_t)(seg.in_off + base + l) * ld + 2 * H + head * 64;
+      o0 = fmaf(pk, vrow[lane], o0);
+      o1 = fmaf(pk, vrow[lane + 32], o1);
+    }
+  }
+  float* orow = ctx + (size_t)(seg.in_off + qi) * H + head * 64;
+  orow[lane] = o0;
+  orow[lane + 32] = o1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BiLSTM recurrence (hidden 256 per direction).  gx = x W_ih^T + b_ih + b_hh for both directions ([rows][2048],
+// gate order i,f,g,o per direction) comes from the GEMM kernel; this kernel runs the serial part:
+// one CTA per (utterance, direction), one thread per gate row, W_hh^T ([dir][256][1024]) streamed from L2
+// with coalesced loads, h broadcast from shared memory.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) lstm_kernel(const float* __restrict__ gx, const float* __restrict__ whhT, const float* __restrict__ bias,
+                                                    float* __restrict__ y, int ldy, const LstmSeg* __restrict__ segs) {
+  __shared__ __align__(16) float h[256];
+  __shared__ float pre[1024];
+  const LstmSeg seg = segs[blockIdx.x];
+  const int dir = blockIdx.y;
+  const int g = threadIdx.x;
+  const float* W = whhT + (size_t)dir * 256 * 1024 + g;
+  const float bg = bias[dir * 1024 + g];
+  float c = 0.f;
+  if (g < 256) h[g] = 0.f;
+  __syncthreads();
+  const int npre = dir ? seg.pre : 0;
+  const int steps = seg.len + npre;
+  for (int s = 0; s < steps; ++s) {
+    const bool is_pad = s < npre;
+    const int t = dir ? (seg.len - 1 - (s - npre)) : s;
+    float a0 = is_pad ? bg : gx[(size_t)(seg.off + t) * 2048 + dir * 1024 + g];
+    float a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 256; k += 4) {
+      const float4 hv = *reinterpret_cast<const float4*>(&h[k]);
+      a0 = fmaf(W[(size_t)(k + 0) * 1024], hv.x, a0);
+      a1 = fmaf(W[(size_t)(k + 1) * 1024], hv.y, a1);
+      a2 = fmaf(W[(size_t)(k + 2) * 1024], hv.z, a2);
+      a3 = fmaf(W[(size_t)(k + 3) * 1024], hv.w, a3);
+    }
+    pre[g] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (g < 256) {
+      const float ig = sigmoidf_acc(pre[g]);
+      const float fg = sigmoidf_acc(pre[256 + g]);
+      const float gg = tanhf(pre[512 + g]);
+      const float og = sigmoidf_acc(pre[768 + g]);
+      c = fg * c + ig * gg;
+      const float hn = og * tanhf(c);
+      h[g] = hn;
+      if (!is_pad) y[(size_t)(seg.off + t) * ldy + dir * 256 + g] = hn;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// duration head: sigmoid -> sum over bins -> / speed -> round-half-even -> clamp(min 1)   (kmodel.py:98-103,115)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void duration_kernel(const float* __restrict__ logits, int ld, int nbins, const int* __restrict__ row2seg,
+                                const float* __restrict__ speeds, float* __restrict__ duration, int* __restrict__ pred_dur, int rows) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int k = 0; k < nbins; ++k) s += sigmoidf_acc(logits[(size_t)row * ld + k]);
+  const float d = __fdiv_rn(s, speeds[row2seg[row]]);
+  duration[row] = d;
+  const float r = rintf(d);            // round half to even == torch.round
+  int n = (int)r;
+  if (n < 1) n = 1;
+  pred_dur[row] = n;
+}
+
+// per-utterance inclusive scan of the integer durations (T <= 512 per utterance)
+__global__ void __launch_bounds__(512) dur_scan_kernel(const int* __restrict__ pred_dur, const Seg* __restrict__ segs, int* __restrict__ cum,
+                                                       int* __restrict__ totals) {
+  __shared__ int buf[512];
+  const Seg seg = segs[blockIdx.x];
+  const int t = threadIdx.x;
+  int carry = 0;
+  for (int base = 0; base < seg.in_len; base += 512) {
+    const int i = base + t;
+    int v = (i < seg.in_len) ? pred_dur[seg.in_off + i] : 0;
+    buf[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 512; o <<= 1) {
+      int add = (t >= o) ? buf[t - o] : 0;
+      __syncthreads();
+      buf[t] += add;
+      __syncthreads();
+    }
+    if (i < seg.in_len) cum[seg.in_off + i] = carry + buf[t];
+    carry += buf[511];
+    __syncthreads();
+  }
+  if (t == 0) totals[blockIdx.x] = carry;
+}
+
+// alignment index map: indices[f] = token whose run covers frame f  (== repeat_interleave(arange(T), pred_dur), kmodel.py:116-119)
+// segs here: in = token rows, out = frame rows.
+__global__ void indices_kernel(const int* __restrict__ cum, const Seg* __restrict__ segs, int* __restrict__ indices, int total_frames,
+                               const int* __restrict__ frame2seg) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= total_frames) return;
+  const Seg seg = segs[frame2seg[f]];
+  const int lf = f - seg.out_off;
+  const int* c = cum + seg.in_off;
+  int lo = 0, hi = seg.in_len - 1;      // first token with cum[token] > lf
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (c[mid] > lf) hi = mid; else lo = mid + 1;
+  }
+  indices[f] = lo;
+}
+
+// length regulation: dst[f, :] = src[token_row(indices[f]), :]   (the one-hot matmuls of kmodel.py:132,139 are this gather)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int lds, const int* __restrict__ indices,
+                                                          const int* __restrict__ frame2seg, const Seg* __restrict__ segs,
+                                                          float* __restrict__ dst, int ldd, int C4, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const Seg seg = segs[frame2seg[row]];
+  const float4* s = reinterpret_cast<const float4*>(src + (size_t)(seg.in_off + indices[row]) * lds);
+  float4* d = reinterpret_cast<float4*>(dst + (size_t)row * ldd);
+  for (int c = lane; c < C4; c += 32) d[c] = s[c];
+}
+
+}  // namespace
+
+cudaError_t launch_layernorm(const float* x, int ldx, const float* res, int ldr, float* out, int ldo, int rows, int C, float eps,
+                             int mode, const float* gamma, const float* beta, const float* gb, int ld_gb, const int* row2seg,
+                             int act, float slope, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  if (C > 32 * MAXV) return cudaErrorInvalidValue;
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ldx, res, ldr, out, ldo, rows, C, eps, mode, gamma, beta, gb, ld_gb, row2seg, act, slope);
+  return launched();
+}
+cudaError_t launch_albert_embed(const int* ids, const int* pos, const float* word, const float* posw, const float* type0,
+                                const float* g, const float* b, float* out, int rows, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  albert_embed_kernel<<<(rows + 7) / 8, 256, 0, s>>>(ids, pos, word, posw, type0, g, b, out, rows);
+  return launched();
+}
+cudaError_t launch_embedding(const int* ids, const float* table, int C, float* out, int ldo, int rows, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  embedding_kernel<<<rows, 128, 0, s>>>(ids, table, C, out, ldo, rows);
+  return launched();
+}
+cudaError_t launch_fill_style(const float* style, int ld_style, int style_off, const int* row2seg, float* out, int ldo, int col_off, int C,
+                              int rows, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  fill_style_kernel<<<rows, 128, 0, s>>>(style, ld_style, style_off, row2seg, out, ldo, col_off, C, rows);
+  return launched();
+}
+cudaError_t launch_attention(const float* qkv, float* ctx, const Seg* segs, int nseg, int max_len, int heads, cudaStream_t s) {
+  if (nseg <= 0 || max_len <= 0) return cudaSuccess;
+  if (max_len > 32 * ATT_MAXK) return cudaErrorInvalidValue;
+  dim3 grid((max_len + 7) / 8, heads, nseg);
+  attention_kernel<<<grid, 256, 0, s>>>(qkv, ctx, segs, heads);
+  return launched();
+}
+cudaError_t launch_lstm(const float* gx, const float* whhT, const float* bias, float* y, int ldy, const LstmSeg* segs, int nseg, cudaStream_t s) {
+  if (nseg <= 0) return cudaSuccess;
+  dim3 grid(nseg, 2);
+  lstm_kernel<<<grid, 1024, 0, s>>>(gx, whhT, bias, y, ldy, segs);
+  return launched();
+}
+cudaError_t launch_duration(const float* logits, int ld, int nbins, const int* row2seg, const float* speeds, float* duration, int* pred_dur,
+                            int rows, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  duration_kernel<<<(rows + 127) / 128, 128, 0, s>>>(logits, ld, nbins, row2seg, speeds, duration, pred_dur, rows);
+  return launched();
+}
+cudaError_t launch_dur_scan(const int* pred_dur, const Seg* segs, int nseg, int* cum, int* totals, cudaStream_t s) {
+  if (nseg <= 0) return cudaSuccess;
+  dur_scan_kernel<<<nseg, 512, 0, s>>>(pred_dur, segs, cum, totals);
+  return launched();
+}
+cudaError_t launch_indices(const int* cum, const Seg* segs, int nseg, int* indices, int total_frames, const int* frame2seg, cudaStream_t s) {
+  if (total_frames <= 0) return cudaSuccess;
+  indices_kernel<<<(total_frames + 255) / 256, 256, 0, s>>>(cum, segs, indices, total_frames, frame2seg);
+  return launched();
+}
+cudaError_t launch_gather_rows(const float* src, int lds, const int* indices, const int* frame2seg, const Seg* segs, float* dst, int ldd,
+                               int C, int rows, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  if ((C & 3) || (lds & 3) || (ldd & 3)) return cudaErrorInvalidValue;
+  gather_rows_kernel<<<(rows + 7) / 8, 256, 0, s>>>(src, lds, indices, frame2seg, segs, dst, ldd, C / 4, rows);
+  return launched();
+}
+
+}  // namespace ttsb

@@ -1,0 +1,106 @@
+"""Stage-by-stage comparison of the CUDA engine with the CPU oracle (run on a GPU box):
+    python tests/parity_report.py [single|pair|batch4] [fp32|bf16]
+Prints max-abs / relative error per tap so a divergence can be localised in one run."""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from oracle.kokoro_oracle import make_noise  # noqa: E402
+from oracle.synth_weights import build_oracle, random_ids, synthetic_voice_pack, workload  # noqa: E402
+
+
+def cases(name):
+    if name == "single":
+        return workload("single")
+    g = torch.Generator().manual_seed(11)
+    lens = {"pair": [20, 33], "batch4": [12, 40, 25, 40]}[name]
+    ids = [random_ids(g, n) for n in lens]
+    pack = synthetic_voice_pack(1)
+    ref = torch.stack([pack[n - 1, 0] for n in lens])
+    return dict(ids=ids, ref_s=ref, speeds=[1.0, 0.9, 1.1, 1.0][: len(lens)])
+
+
+def rel(a, b):
+    d = (a - b).abs().max().item()
+    s = b.abs().max().item() + 1e-12
+    return d, d / s
+
+
+def main():
+    name = sys.argv[1] if len(sys.argv) > 1 else "single"
+    prec = sys.argv[2] if len(sys.argv) > 2 else "fp32"
+    import illufly_tts_b200 as pkg
+    m = build_oracle(1234)
+    w = cases(name)
+    t = time.time()
+    o = m.forward_batch(w["ids"], w["ref_s"], w["speeds"], noise_seed=0, want_taps=True)
+    print(f"oracle: {time.time() - t:.2f}s  frames={[int(p.sum()) for p in o.pred_dur]}")
+    eng = pkg.Engine(m.export_checkpoint(), 0, pkg.PRECISION_BF16 if prec == "bf16" else pkg.PRECISION_FP32)
+    eng.enable_taps(True)
+    B = len(w["ids"])
+    # durations first (no noise needed), then the full run with the oracle's noise
+    noise = [make_noise(0, i, int(o.pred_dur[i].sum())) for i in range(B)]
+    forced = [p.tolist() for p in o.pred_dur]
+    t = time.time()
+    r = eng.synthesize(w["ids"], w["ref_s"], w["speeds"], noise=noise, want_indices=True, forced_dur=forced)
+    torch.cuda.synchronize()
+    print(f"engine: {time.time() - t:.3f}s  launches={eng.launch_count()}")
+    ok = True
+    for i in range(B):
+        same = torch.equal(r.pred_dur[i], o.pred_dur[i])
+        margin = (o.duration[i] - o.duration[i].floor() - 0.5).abs().min().item()
+        dd = (r.duration[i] - o.duration[i]).abs().max().item()
+        print(f"utt {i}: pred_dur equal={same} (|dur diff| max {dd:.2e}, oracle margin to .5 {margin:.3e}); indices equal={torch.equal(r.indices[i], o.indices[i])}")
+        ok &= same
+    # taps: engine taps are ragged-concatenated channels-last; oracle taps are per utterance channels-first
+    Ts = [len(x) for x in w["ids"]]
+    Fs = [int(p.sum()) for p in o.pred_dur]
+
+    def cat_oracle(key, cl=True):
+        parts = []
+        for i in range(B):
+            v = o.taps[i][key]
+            if v.dim() == 3:
+                v = v[0]
+            if v.dim() == 1:
+                v = v[:, None]
+            elif cl:
+                v = v.t()
+            parts.append(v)
+        return torch.cat(parts, 0)
+
+    for key, okey, cl in [("d", "d", False), ("t_en", "t_en", True), ("en", "en", True), ("asr", "asr", True), ("F0", "F0", True), ("N", "N", True),
+                          ("gen_in", "gen_in", True), ("har_source", "har_source", True), ("har", "har", True), ("gen_stage0", "gen_stage0", True),
+                          ("gen_stage1", "gen_stage1", True), ("conv_post", "conv_post", True)]:
+        try:
+            a = eng.read_tap(key)
+        except Exception as exc:
+            print(f"{key:12s} <no tap: {exc}>")
+            continue
+        b = cat_oracle(okey, cl)
+        if a.shape != b.shape:
+            print(f"{key:12s} SHAPE engine {tuple(a.shape)} oracle {tuple(b.shape)}")
+            continue
+        d, rr = rel(a, b)
+        worst = (a - b).abs().flatten().argmax().item()
+        print(f"{key:12s} shape {tuple(a.shape)} max-abs {d:.3e} rel {rr:.3e} (worst at row {worst // a.shape[1]}, col {worst % a.shape[1]}) nan={bool(torch.isnan(a).any())}")
+    for i in range(B):
+        a, b = r.audio[i].cpu(), o.audio[i]
+        if a.shape != b.shape:
+            print(f"audio {i}: SHAPE {tuple(a.shape)} vs {tuple(b.shape)}")
+            continue
+        err = (a - b)
+        snr = 10 * torch.log10((b ** 2).sum() / (err ** 2).sum().clamp_min(1e-30)).item()
+        print(f"audio {i}: n={a.numel()} max-abs {err.abs().max().item():.3e} snr {snr:.1f} dB  (|ref| max {b.abs().max().item():.3f})")
+    # predicted (not forced) durations through the whole path
+    r2 = eng.synthesize(w["ids"], w["ref_s"], w["speeds"], noise=None, seed=1)
+    print("unforced run frames:", [int(a.numel()) // 600 for a in r2.audio], "oracle:", Fs, "tokens:", Ts)
+
+
+if __name__ == "__main__":
+    main()
