@@ -431,9 +431,15 @@ class Generator(nn.Module):
     def istft(self, mag, phase):
         return torch.istft(mag * torch.exp(phase * 1j), self.n_fft, self.hop, self.n_fft, window=self.window)
 
-    def forward(self, x, s, f0, noise, taps=None):
+    def forward(self, x, s, f0, noise, taps=None, frame0_phase=None):
         har_source = self.m_source(f0, noise)
         mag, ang = self.stft(har_source)
+        if frame0_phase is not None:
+            # STFT frame 0 is exactly symmetric (reflect padding about sample 0), so Im X_k(0) is pure rounding noise and
+            # angle() is +-pi by the SIGN of that noise wherever Re < 0: FFT-library dependent, not a property of the model.
+            # Parity runs pin those 11 values to the implementation under test (tests/, DESIGN.md "ill-conditioned points").
+            ang = ang.clone()
+            ang[:, :, 0] = frame0_phase
         har = torch.cat([mag, ang], dim=1)
         if taps is not None:
             taps["har_source"], taps["har"] = har_source, har
@@ -473,7 +479,7 @@ class Decoder(nn.Module):
         self.asr_res = nn.Sequential(weight_norm(nn.Conv1d(512, 64, 1)))
         self.generator = Generator(c)
 
-    def forward(self, asr, F0_curve, N, s, noise, taps=None):
+    def forward(self, asr, F0_curve, N, s, noise, taps=None, frame0_phase=None):
         F0 = self.F0_conv(F0_curve[:, None])
         Nn = self.N_conv(N[:, None])
         x = self.encode(torch.cat([asr, F0, Nn], dim=1), s)
@@ -487,7 +493,7 @@ class Decoder(nn.Module):
                 res = False
         if taps is not None:
             taps["gen_in"] = x
-        return self.generator(x, s, F0_curve, noise, taps)
+        return self.generator(x, s, F0_curve, noise, taps, frame0_phase)
 
 
 # --------------------------------------------------------------------------------------
@@ -595,9 +601,9 @@ class KokoroOracle(nn.Module):
         return out
 
     @torch.no_grad()
-    def vocoder(self, x, s, f0, noise):
+    def vocoder(self, x, s, f0, noise, taps=None, frame0_phase=None):
         """Generator only (BASELINE config 4): x [B,512,L], s [B,128], f0 [B,L], noise [B,300L,9]."""
-        return self.decoder.generator(x, s, f0, noise).squeeze(1)
+        return self.decoder.generator(x, s, f0, noise, taps, frame0_phase).squeeze(1)
 
 
 def make_noise(seed: int, utt: int, frames: int) -> torch.Tensor:

@@ -31,6 +31,69 @@ def rel(a, b):
     return d, d / s
 
 
+def describe(key, a, b):
+    if a.shape != b.shape:
+        print(f"{key:12s} SHAPE engine {tuple(a.shape)} oracle {tuple(b.shape)}")
+        return
+    e = (a - b).abs()
+    d, rr = rel(a, b)
+    worst = e.flatten().argmax().item()
+    rms = (e.double() ** 2).mean().sqrt().item()
+    frac = (e > 1e-3 * (b.abs().max().item() + 1e-12)).double().mean().item()
+    nz = int((e > 0).sum())
+    print(f"{key:12s} shape {tuple(a.shape)} max-abs {d:.3e} rel {rr:.3e} rms {rms:.3e} frac(>1e-3 rel) {frac:.2e} n_differ {nz} "
+          f"(worst at row {worst // a.shape[1]}, col {worst % a.shape[1]}) nan={bool(torch.isnan(a).any())}")
+
+
+def vocoder_report(m, eng, o, w):
+    """generator only, fed with the oracle's own gen_in / F0 (bit-identical inputs)"""
+    B = len(w["ids"])
+    Fs = [int(p.sum()) for p in o.pred_dur]
+    Lmax = 2 * max(Fs)
+    x = torch.zeros(B, 512, Lmax)
+    f0 = torch.zeros(B, Lmax)
+    nz = torch.zeros(B, 300 * Lmax, 9)
+    for i in range(B):
+        L = 2 * Fs[i]
+        x[i, :, :L] = o.taps[i]["gen_in"][0]
+        f0[i, :L] = o.taps[i]["F0"]
+        nz[i, : 300 * L] = make_noise(0, i, Fs[i])
+    s = w["ref_s"][:, :128]
+    audio = eng.vocoder(x, s, f0, nz, lengths=[2 * f for f in Fs])
+    print("---- vocoder only, oracle inputs ----")
+    for key in ["har_source", "har", "gen_stage0", "gen_stage1", "conv_post"]:
+        a = eng.read_tap(key)
+        parts = []
+        for i in range(B):
+            v = o.taps[i][key]
+            v = v[0] if v.dim() == 3 else v
+            v = v[:, None] if v.dim() == 1 else v.t()
+            parts.append(v)
+        describe(key, a, torch.cat(parts, 0))
+    har_e = eng.read_tap("har")
+    row = 0
+    for i in range(B):
+        a, b = audio[i].cpu(), o.audio[i]
+        err = a - b
+        snr = 10 * torch.log10((b ** 2).sum() / (err ** 2).sum().clamp_min(1e-30)).item()
+        prof = [f"{err[k * len(err) // 8:(k + 1) * len(err) // 8].abs().max().item():.1e}" for k in range(8)]
+        print(f"audio {i}: n={a.numel()} max-abs {err.abs().max().item():.3e} snr {snr:.1f} dB profile {prof}")
+        # oracle with the degenerate STFT frame 0 pinned to the engine's phases
+        L = 2 * Fs[i]
+        t2 = {}
+        b2 = m.vocoder(x[i:i + 1, :, :L], s[i:i + 1], f0[i:i + 1, :L], nz[i:i + 1, :300 * L], t2, har_e[row, 11:22][None])[0]
+        err = a - b2
+        prof = [f"{err[k * len(err) // 8:(k + 1) * len(err) // 8].abs().max().item():.1e}" for k in range(8)]
+        print(f"   vs oracle with frame-0 phase pinned: max-abs {err.abs().max().item():.3e} profile {prof}")
+        nrow = 60 * L + 1
+        for key in ["gen_stage0", "gen_stage1", "conv_post"]:
+            aa = eng.read_tap(key)
+            r0 = {"gen_stage0": (row - i) // 6, "gen_stage1": row, "conv_post": row}[key]
+            n = {"gen_stage0": 10 * L, "gen_stage1": nrow, "conv_post": nrow}[key]
+            describe("  " + key, aa[r0:r0 + n], t2[key][0].t())
+        row += nrow
+
+
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "single"
     prec = sys.argv[2] if len(sys.argv) > 2 else "fp32"
@@ -82,13 +145,7 @@ def main():
         except Exception as exc:
             print(f"{key:12s} <no tap: {exc}>")
             continue
-        b = cat_oracle(okey, cl)
-        if a.shape != b.shape:
-            print(f"{key:12s} SHAPE engine {tuple(a.shape)} oracle {tuple(b.shape)}")
-            continue
-        d, rr = rel(a, b)
-        worst = (a - b).abs().flatten().argmax().item()
-        print(f"{key:12s} shape {tuple(a.shape)} max-abs {d:.3e} rel {rr:.3e} (worst at row {worst // a.shape[1]}, col {worst % a.shape[1]}) nan={bool(torch.isnan(a).any())}")
+        describe(key, a, cat_oracle(okey, cl))
     for i in range(B):
         a, b = r.audio[i].cpu(), o.audio[i]
         if a.shape != b.shape:
@@ -97,6 +154,7 @@ def main():
         err = (a - b)
         snr = 10 * torch.log10((b ** 2).sum() / (err ** 2).sum().clamp_min(1e-30)).item()
         print(f"audio {i}: n={a.numel()} max-abs {err.abs().max().item():.3e} snr {snr:.1f} dB  (|ref| max {b.abs().max().item():.3f})")
+    vocoder_report(m, eng, o, w)
     # predicted (not forced) durations through the whole path
     r2 = eng.synthesize(w["ids"], w["ref_s"], w["speeds"], noise=None, seed=1)
     print("unforced run frames:", [int(a.numel()) // 600 for a in r2.audio], "oracle:", Fs, "tokens:", Ts)
