@@ -460,11 +460,17 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   a.ostats = c.ostats; a.ld_ostats = c.w->Cout;
   a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
   if (c.pro >= PRO_ADAIN_LRELU && (!c.pstats || !c.gb)) { set_error("internal: AdaIN prologue without statistics"); return TTSB_E_INVALID; }
+  const double rows = (double)t.out_rows;
+  const double fl = 2.0 * rows * a.Cin * a.Cout * a.k;
+  const double by = 4.0 * rows * ((double)a.Cout * (1 + (a.res ? 1 : 0) + (a.accumulate ? 1 : 0))) + 4.0 * (double)t.in_rows * a.Cin;
   if (c.tensor && r.e.precision == TTSB_PRECISION_BF16 && conv_umma_supported(a)) {
+    r.e.prof.begin(r.s, PROF_CONV_TENSOR, fl, by);
     CK(launch_conv_umma(a, r.s));
   } else {
+    r.e.prof.begin(r.s, PROF_CONV_SIMT, fl, by);
     CK(launch_conv_simt(a, r.s));
   }
+  r.e.prof.end(r.s);
   return TTSB_OK;
 }
 
@@ -472,7 +478,9 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
 int run_bilstm(Run& r, const LstmW& l, const float* x, int ldx, float* gx, float* y, int ldy, const SegTab& t, const LstmSeg* lsegs) {
   ConvCall c; c.w = &l.ih; c.x = x; c.ldx = ldx; c.y = gx; c.ldy = 2048;
   RC(run_conv(r, c, t));
+  r.e.prof.begin(r.s, PROF_LSTM, 2.0 * t.out_rows * 2 * 1024 * 256, 0.0);
   CK(launch_lstm(gx, l.whhT, l.ih.bias, y, ldy, lsegs, t.nseg, r.s));
+  r.e.prof.end(r.s);
   return TTSB_OK;
 }
 
@@ -602,7 +610,9 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
     ConvCall cu; cu.w = &e.ups[i]; cu.x = xin; cu.ldx = e.ups[i].Cin; cu.y = up; cu.ldy = s_up * C; cu.pad = 1; cu.pro = PRO_LRELU; cu.slope = 0.1f; cu.tensor = true;
     RC(run_conv(r, cu, i == 0 ? tL_U0 : tS0_U1));
     const SegTab& tUS = i == 0 ? tU0_S0 : tU1_S1;
+    e.prof.begin(r.s, PROF_ELEMENTWISE, 0.0, 12.0 * (double)n);
     CK(launch_up_add(up, C, s_up / 2, i == 1, xs2, C, x0, C, C, tUS.segs, nseg, tUS.max_out, st_x0, C, r.s));
+    e.prof.end(r.s);
     // mean of the three parallel AdaINResBlock1
     float* acc = r.alloc<float>(n);
     float* cur = r.alloc<float>(n);
@@ -620,7 +630,9 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   ConvCall cpc; cpc.w = &e.conv_post; cpc.x = stage_out; cpc.ldx = 128; cpc.y = cp; cpc.ldy = 24; cpc.pad = 3; cpc.pro = PRO_LRELU; cpc.slope = 0.01f; cpc.tensor = true;
   RC(run_conv(r, cpc, tS1));
   RC(r.tap("conv_post", cp, spS1.total, 22, 24));
+  e.prof.begin(r.s, PROF_ISTFT, 0.0, 4.0 * (22.0 * spS1.total + (double)spA.total));
   CK(launch_istft(cp, 24, audio, tS1_A.segs, nseg, spS1.maxlen, r.s));
+  e.prof.end(r.s);
   return TTSB_OK;
 }
 
@@ -651,6 +663,8 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   e.begun = false;
   e.arena.reset();
   Run r(e);
+  e.prof.reset();
+  CK(cudaEventRecord(e.ev_step0, r.s));
   std::vector<int> lens(B);
   int Tmax = 0;
   for (int b = 0; b < B; ++b) {
@@ -831,9 +845,13 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   if (!d_idx || !EN || !CAT0) return TTSB_E_NOMEM;
   CK(launch_indices(e.d_cum, tTF.segs, B, d_idx, RF, d_f2s, r.s));
   if (indices) CK(cudaMemcpyAsync(indices, d_idx, sizeof(int) * RF, cudaMemcpyDeviceToHost, r.s));
+  e.prof.begin(r.s, PROF_GATHER, 0.0, 4.0 * 640 * ((double)RF + spT.total) + 8.0 * RF);
   CK(launch_gather_rows(e.d_X, 640, d_idx, d_f2s, tTF.segs, EN, 640, 640, RF, r.s));
+  e.prof.end(r.s);
   CK(cudaMemsetAsync(CAT0, 0, sizeof(float) * (size_t)RF * 516, r.s));
+  e.prof.begin(r.s, PROF_GATHER, 0.0, 4.0 * 512 * ((double)RF + spT.total) + 8.0 * RF);
   CK(launch_gather_rows(e.d_ten, 512, d_idx, d_f2s, tTF.segs, CAT0, 516, 512, RF, r.s));
+  e.prof.end(r.s);
   RC(r.tap("en", EN, RF, 640, 640));
   RC(r.tap("asr", CAT0, RF, 512, 516));
 
@@ -914,11 +932,11 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
     if (!d_audio) return TTSB_E_NOMEM;
   }
   RC(run_generator(r, spL, GIN, F0, gbD, ldD, d_noise, seed, d_audio));
-  if (audio_mem != TTSB_MEM_DEVICE) {
-    CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * (size_t)RF * 600, cudaMemcpyDeviceToHost, r.s));
+  if (audio_mem != TTSB_MEM_DEVICE) CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * (size_t)RF * 600, cudaMemcpyDeviceToHost, r.s));
+  CK(cudaEventRecord(e.ev_step1, r.s));
+  if (audio_mem != TTSB_MEM_DEVICE || indices || e.taps_on || e.prof.on) {
     CK(cudaStreamSynchronize(r.s));
-  } else if (indices || e.taps_on) {
-    CK(cudaStreamSynchronize(r.s));
+    e.prof.collect();
   }
   return TTSB_OK;
 }
@@ -934,6 +952,8 @@ int engine_vocoder(Engine& e, const float* x, const float* f0, const float* styl
   e.begun = false;
   e.arena.reset();
   Run r(e);
+  e.prof.reset();
+  CK(cudaEventRecord(e.ev_step0, r.s));
   std::vector<int> lL(B);
   for (int b = 0; b < B; ++b) {
     lL[b] = l_offsets[b + 1] - l_offsets[b];
@@ -965,9 +985,11 @@ int engine_vocoder(Engine& e, const float* x, const float* f0, const float* styl
     if (!d_audio) return TTSB_E_NOMEM;
   }
   RC(run_generator(r, spL, dx, df0, gbD, e.style_dec.ldw, dnoise, seed, d_audio));
-  if (audio_mem != TTSB_MEM_DEVICE) {
-    CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * RL * 300, cudaMemcpyDeviceToHost, r.s));
+  if (audio_mem != TTSB_MEM_DEVICE) CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * RL * 300, cudaMemcpyDeviceToHost, r.s));
+  CK(cudaEventRecord(e.ev_step1, r.s));
+  if (audio_mem != TTSB_MEM_DEVICE || e.taps_on || e.prof.on) {
     CK(cudaStreamSynchronize(r.s));
+    e.prof.collect();
   }
   return TTSB_OK;
 }

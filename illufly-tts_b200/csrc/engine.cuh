@@ -60,6 +60,38 @@ struct SegTab {                           // device tables for one (in space -> 
 
 struct Tap { float* d = nullptr; int64_t rows = 0, cols = 0; };
 
+// per-category device time of the last step, from CUDA events recorded around the launches on the engine's stream
+enum ProfCat : int { PROF_CONV_TENSOR = 0, PROF_CONV_SIMT = 1, PROF_LSTM = 2, PROF_ISTFT = 3, PROF_ELEMENTWISE = 4, PROF_GATHER = 5, PROF_NCAT = 6 };
+struct ProfRec { int cat; double flops, bytes; };
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> events;
+  std::vector<ProfRec> recs;
+  double ms[PROF_NCAT] = {0}, flops[PROF_NCAT] = {0}, bytes[PROF_NCAT] = {0};
+  long long launches[PROF_NCAT] = {0};
+  void begin(cudaStream_t s, int cat, double fl, double by) {
+    if (!on) return;
+    const size_t i = recs.size();
+    while (events.size() < 2 * (i + 1)) { cudaEvent_t ev; if (cudaEventCreate(&ev) != cudaSuccess) { on = false; return; } events.push_back(ev); }
+    recs.push_back({cat, fl, by});
+    cudaEventRecord(events[2 * i], s);
+  }
+  void end(cudaStream_t s) {
+    if (!on || recs.empty()) return;
+    cudaEventRecord(events[2 * (recs.size() - 1) + 1], s);
+  }
+  void reset() { recs.clear(); for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = flops[c] = bytes[c] = 0; launches[c] = 0; } }
+  void collect() {   // call after the stream has drained
+    for (size_t i = 0; i < recs.size(); ++i) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, events[2 * i], events[2 * i + 1]) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+      ms[recs[i].cat] += t; flops[recs[i].cat] += recs[i].flops; bytes[recs[i].cat] += recs[i].bytes; launches[recs[i].cat] += 1;
+    }
+    recs.clear();
+  }
+  void release() { for (auto ev : events) cudaEventDestroy(ev); events.clear(); }
+};
+
 class Arena {
  public:
   ~Arena() { release(); }
@@ -76,7 +108,8 @@ class Arena {
 struct Engine {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr, ev_step0 = nullptr, ev_step1 = nullptr;
+  Profiler prof;
   int precision = 0;
   bool taps_on = false;
   bool finalized = false;

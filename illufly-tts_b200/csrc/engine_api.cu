@@ -97,6 +97,8 @@ int ttsb_engine_create(int cuda_device, ttsb_engine** out) {
   CKA(cudaEventCreate(&h->e.ev0));
   CKA(cudaEventCreate(&h->e.ev1));
   CKA(cudaEventCreateWithFlags(&h->e.ev_sync, cudaEventDisableTiming));
+  CKA(cudaEventCreate(&h->e.ev_step0));
+  CKA(cudaEventCreate(&h->e.ev_step1));
   *out = h;
   return TTSB_OK;
 }
@@ -113,6 +115,9 @@ int ttsb_engine_destroy(ttsb_engine* h) {
   if (e.ev0) cudaEventDestroy(e.ev0);
   if (e.ev1) cudaEventDestroy(e.ev1);
   if (e.ev_sync) cudaEventDestroy(e.ev_sync);
+  if (e.ev_step0) cudaEventDestroy(e.ev_step0);
+  if (e.ev_step1) cudaEventDestroy(e.ev_step1);
+  e.prof.release();
   if (e.stream) cudaStreamDestroy(e.stream);
   delete h;
   return TTSB_OK;
@@ -150,6 +155,28 @@ int ttsb_engine_enable_taps(ttsb_engine* h, int on) {
   return TTSB_OK;
 }
 int64_t ttsb_engine_launch_count(ttsb_engine* h) { (void)h; return (int64_t)g_launches; }
+
+int ttsb_engine_last_step_ms(ttsb_engine* h, float* ms) {
+  if (!h || !ms) { set_error("last_step_ms: bad arguments"); return TTSB_E_INVALID; }
+  CKA(cudaSetDevice(h->e.device));
+  CKA(cudaEventSynchronize(h->e.ev_step1));
+  CKA(cudaEventElapsedTime(ms, h->e.ev_step0, h->e.ev_step1));
+  return TTSB_OK;
+}
+int ttsb_engine_profile(ttsb_engine* h, int on) {
+  if (!h) return TTSB_E_INVALID;
+  h->e.prof.on = on != 0;
+  return TTSB_OK;
+}
+int ttsb_engine_profile_read(ttsb_engine* h, int category, double* ms, double* flops, double* bytes, int64_t* launches) {
+  if (!h || category < 0 || category >= PROF_NCAT) { set_error("profile_read: bad arguments"); return TTSB_E_INVALID; }
+  const Profiler& p = h->e.prof;
+  if (ms) *ms = p.ms[category];
+  if (flops) *flops = p.flops[category];
+  if (bytes) *bytes = p.bytes[category];
+  if (launches) *launches = p.launches[category];
+  return TTSB_OK;
+}
 
 int ttsb_synthesize_begin(ttsb_engine* h, const int32_t* ids, const int32_t* token_offsets, int B, const float* ref_s, const float* speeds,
                           int padded_lstm, const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets) {

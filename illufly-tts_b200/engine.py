@@ -95,6 +95,24 @@ class Engine:
     def launch_count(self) -> int:
         return int(self._lib.ttsb_engine_launch_count(self._h))
 
+    def last_step_ms(self) -> float:
+        ms = C.c_float(0)
+        _lib.check(self._lib.ttsb_engine_last_step_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    PROFILE_CATEGORIES = ("conv_tensor", "conv_fp32", "lstm", "istft", "upsample_add", "gather")
+
+    def profile(self, on: bool = True):
+        _lib.check(self._lib.ttsb_engine_profile(self._h, int(on)))
+
+    def profile_read(self) -> Dict[str, Dict[str, float]]:
+        out = {}
+        for i, name in enumerate(self.PROFILE_CATEGORIES):
+            ms, fl, by, n = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int64(0)
+            _lib.check(self._lib.ttsb_engine_profile_read(self._h, i, C.byref(ms), C.byref(fl), C.byref(by), C.byref(n)))
+            out[name] = dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=int(n.value))
+        return out
+
     def read_tap(self, name: str) -> torch.Tensor:
         rows, cols = C.c_int64(), C.c_int64()
         _lib.check(self._lib.ttsb_engine_read_tap(self._h, name.encode(), None, C.byref(rows), C.byref(cols)))

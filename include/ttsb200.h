@@ -82,6 +82,14 @@ TTSB_API int ttsb_engine_enable_taps(ttsb_engine* e, int on);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 TTSB_API int64_t ttsb_engine_launch_count(ttsb_engine* e);
 
+/* device time (ms) of the last synthesis / vocoder step: CUDA events on the engine's stream from the first launch of
+ * begin() (or vocoder()) to the last operation of finish(), host gaps between the two phases included */
+TTSB_API int ttsb_engine_last_step_ms(ttsb_engine* e, float* ms);
+/* per-kernel-category CUDA-event timing of the next steps (bench.py's roofline): category 0 tcgen05 conv, 1 fp32 conv,
+ * 2 LSTM recurrence, 3 iSTFT, 4 upsample-add (elementwise), 5 length-regulation gather.  Results are those of the last step. */
+TTSB_API int ttsb_engine_profile(ttsb_engine* e, int on);
+TTSB_API int ttsb_engine_profile_read(ttsb_engine* e, int category, double* ms, double* flops, double* bytes, int64_t* launches);
+
 /* ---- the hot path, two-phase because the number of frames is data-dependent ---------------------------
  * replaces: BatchKModel.forward_batch (core/kmodel.py:7-150) and the inherited KModel.forward
  *           (core/pipeline.py:204); ids are already mapped through the vocab and wrapped in 0 ... 0
