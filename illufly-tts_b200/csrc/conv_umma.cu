@@ -1,7 +1,444 @@
-// placeholder, replaced below by the tcgen05 kernel
+// tcgen05 implicit-GEMM 1-D convolution over ragged channels-last rows (sm_100a only).
+//
+//   D[time (M = 128 TMEM lanes), Cout tile (N <= 256 TMEM columns)] += A[time + tap*dil - pad, Cin chunk] * W[tap][Cin chunk][Cout]
+//
+// * A operand: the CTA's producer warps read the fp32 activations once (128 + halo rows x up to 128 channels per "slab"),
+//   apply the fused prologue (InstanceNorm normalise + AdaIN affine + Snake | LeakyReLU) and write bf16 into shared memory in
+//   the no-swizzle K-major UMMA layout [channel-chunk plane][row][8 ch = 16 B].  A tap is then just a row offset of the
+//   operand descriptor's start address (row * 16 B) — one slab serves all k taps, no im2col, no re-read.
+// * B operand: weights pre-packed on the host into the exact shared-memory image of one (tap, 64-channel) stage, streamed by
+//   the bulk-copy engine (cp.async.bulk, UBLKCP) through a 3-stage mbarrier ring.
+// * MMA: one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 x N x K16, bf16 x bf16 -> fp32 in TMEM);
+//   tcgen05.commit releases weight stages / slabs and publishes the accumulator.
+// * Epilogue (the 8 producer warps): tcgen05.ld 32x32b.x32 -> per-warp shared staging tile -> coalesced float4 rows:
+//   + bias, + residual, * scale, (+ running sum of the three parallel resblocks), and per-(utterance, channel) sum / sum of
+//   squares for the NEXT AdaIN, so InstanceNorm never costs a pass of its own.
+// Reference maths: SURVEY.md A.7, A.11, A.12 (kokoro AdainResBlk1d / Generator / AdaINResBlock1).
 #include "common.cuh"
+
 namespace ttsb {
-bool conv_umma_supported(const ConvArgs&) { return false; }
-cudaError_t launch_conv_umma(const ConvArgs&, cudaStream_t) { return cudaErrorNotSupported; }
-void pack_umma_weights(const float*, int, int, int, int, std::vector<__nv_bfloat16>& out, int& cin_pad, int& cout_pad) { out.clear(); cin_pad = cout_pad = 0; }
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int KCH = 64;                 // channels per weight stage
+constexpr int NPW = 8;                  // producer / epilogue warps
+constexpr int NPROD = NPW * 32;
+constexpr int NTHREADS = NPROD + 64;    // + weight-loader warp (8) + MMA warp (9)
+constexpr int NSTAGE = 3;
+constexpr int STG_LD = 36;              // floats per staging row (32 + 4 pad: 16-B aligned rows, conflict-free both ways)
+constexpr int STG_BYTES = 32 * STG_LD * 4;
+constexpr uint32_t SPIN_LIMIT = 40u * 1000u * 1000u;
+
+struct Plan {
+  int BN, KS, nsc, nslab, SR, kcn, tmem_cols, ntile_n;
+  uint32_t off_bar, off_stats, off_par, off_slab, slab_bytes, off_w, wstage_bytes, smem_bytes;
+};
+
+struct UArgs {
+  ConvArgs a;
+  Plan p;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
+      "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory operand descriptor, K-major, no swizzle (layout_type 0), version 1 (Blackwell):
+//   core matrix = 8 rows x 16 B contiguous; LBO = byte distance between the two 16-B K chunks of one K=16 MMA,
+//   SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const ConvArgs& p = u.a;
+  const Plan& pl = u.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Tile tile = p.tiles[blockIdx.x];
+  const Seg seg = p.segs[tile.seg];
+  const int nt = blockIdx.y;
+  const int n0 = nt * pl.BN;
+
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
+  const uint32_t bar0 = smem_u32(smem + pl.off_bar);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
+  auto bar_slab_full = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
+  auto bar_slab_empty = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
+  const uint32_t bar_acc = bar0 + 8u * (2 * NSTAGE + 4);
+  float* s_sum = reinterpret_cast<float*>(smem + pl.off_stats);
+  float* s_sq = s_sum + 256;
+  float* s_par = reinterpret_cast<float*>(smem + pl.off_par);     // [5][cin_pad]: mean, a, b, alpha, 1/alpha
+  const int cpad = p.cin_pad;
+
+  // ---- one-time setup ----
+  if (warp == NPW + 1) tmem_alloc(smem_u32(s_tmem), (uint32_t)pl.tmem_cols);
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_slab_full(b), NPROD); mbar_init(bar_slab_empty(b), 1); }
+    mbar_init(bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (p.pro >= PRO_ADAIN_LRELU) {
+    for (int c = tid; c < cpad; c += NTHREADS) {
+      float mean = 0.f, a = 0.f, b = 0.f, al = 1.f;
+      if (c < p.Cin) {
+        const double* st = p.pstats + ((size_t)tile.seg * p.ld_pstats + c) * 2;
+        adain_coef(st, seg.in_len, p.gb[(size_t)tile.seg * p.ld_gb + c], p.gb[(size_t)tile.seg * p.ld_gb + p.beta_off + c], mean, a, b);
+        if (p.pro == PRO_ADAIN_SNAKE) al = p.alpha[c];
+      }
+      s_par[c] = mean; s_par[cpad + c] = a; s_par[2 * cpad + c] = b; s_par[3 * cpad + c] = al; s_par[4 * cpad + c] = 1.0f / al;
+    }
+  }
+  for (int c = tid; c < 512; c += NTHREADS) s_sum[c] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const int nwst = KCH * 0 + pl.KS / KCH;            // weight stages per (slab, tap)
+  const uint32_t slab0 = smem_u32(smem + pl.off_slab);
+  const uint32_t w0 = smem_u32(smem + pl.off_w);
+
+  if (warp < NPW) {
+    // =================== producers: build the bf16 operand slabs ===================
+    const int planes = pl.KS >> 3;
+    const int rpp = NPROD / planes;                    // rows per pass
+    const int pln = tid % planes, r0 = tid / planes;
+    for (int sc = 0; sc < pl.nsc; ++sc) {
+      const int b = sc % pl.nslab;
+      mbar_wait(bar_slab_empty(b), (((uint32_t)(sc / pl.nslab)) & 1u) ^ 1u);
+      const int c0 = sc * pl.KS + pln * 8;
+      float pm[8], pa[8], pb[8], pal[8], pia[8];
+      if (p.pro >= PRO_ADAIN_LRELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pm[e] = s_par[c0 + e]; pa[e] = s_par[cpad + c0 + e]; pb[e] = s_par[2 * cpad + c0 + e];
+          pal[e] = s_par[3 * cpad + c0 + e]; pia[e] = s_par[4 * cpad + c0 + e];
+        }
+      }
+      uint8_t* slab = smem + pl.off_slab + (size_t)b * pl.slab_bytes + (size_t)pln * pl.SR * 16;
+      for (int r = r0; r < pl.SR; r += rpp) {
+        const int tin = (tile.t0 + r - p.pad) >> p.in_shr;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        const bool valid = (tile.t0 + r - p.pad) >= 0 && tin < seg.in_len && c0 < p.Cin;
+        if (valid) {
+          const float* src = p.x + (size_t)(seg.in_off + tin) * p.ldx + c0;
+          const float4 q0 = *reinterpret_cast<const float4*>(src);
+          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+          if (c0 + 4 < p.ldx) {
+            const float4 q1 = *reinterpret_cast<const float4*>(src + 4);
+            v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x = v[e];
+            if (p.pro == PRO_LRELU) x = lrelu(x, p.slope);
+            else if (p.pro == PRO_ADAIN_LRELU) x = lrelu(fmaf(x - pm[e], pa[e], pb[e]), p.slope);
+            else if (p.pro == PRO_ADAIN_SNAKE) {
+              const float w = fmaf(x - pm[e], pa[e], pb[e]);
+              const float sn = __sinf(pal[e] * w);
+              x = fmaf(pia[e], sn * sn, w);
+            }
+            v[e] = (c0 + e < p.Cin) ? x : 0.f;
+          }
+        }
+        uint4 o;
+        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(slab + (size_t)r * 16) = o;
+      }
+      fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(bar_slab_full(b));
+    }
+
+    // =================== epilogue ===================
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int q = warp & 3, h = warp >> 2;
+    float* stg = reinterpret_cast<float*>(smem + pl.off_slab + (size_t)warp * STG_BYTES);   // aliases slab 0 (all MMAs are done)
+    const int nchunk = pl.BN >> 5;
+    for (int chunk = h; chunk < nchunk; chunk += 2) {
+      const int c0 = chunk * 32;
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 f;
+        f.x = __uint_as_float(v[4 * i]); f.y = __uint_as_float(v[4 * i + 1]); f.z = __uint_as_float(v[4 * i + 2]); f.w = __uint_as_float(v[4 * i + 3]);
+        *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * i) = f;
+      }
+      __syncwarp();
+      float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+      const int cc = (lane & 7) * 4;
+      const int co = n0 + c0 + cc;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3);
+        const int t = tile.t0 + q * 32 + rr;
+        if (t < seg.out_len && co < p.Cout) {
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
+          float x[4] = {a4.x, a4.y, a4.z, a4.w};
+          const size_t orow = (size_t)(seg.out_off + t);
+          float* dst = p.y + orow * p.ldy + co;
+          if (co + 3 < p.Cout) {
+            if (p.bias) { const float4 b4 = *reinterpret_cast<const float4*>(p.bias + co); x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w; }
+            if (p.res) { const float4 r4 = *reinterpret_cast<const float4*>(p.res + orow * p.ldr + co); x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w; }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] *= p.out_scale;
+            if (p.accumulate) { const float4 y4 = *reinterpret_cast<const float4*>(dst); x[0] += y4.x; x[1] += y4.y; x[2] += y4.z; x[3] += y4.w; }
+            *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (co + e < p.Cout) {
+                float xv = x[e];
+                if (p.bias) xv += p.bias[co + e];
+                if (p.res) xv += p.res[orow * p.ldr + co + e];
+                xv *= p.out_scale;
+                if (p.accumulate) xv += dst[e];
+                dst[e] = xv;
+                x[e] = xv;
+              } else x[e] = 0.f;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { ps[e] += x[e]; pq[e] += x[e] * x[e]; }
+        }
+      }
+      __syncwarp();
+      if (p.ostats) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);  pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 8);
+          ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16); pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { atomicAdd(&s_sum[c0 + cc + e], ps[e]); atomicAdd(&s_sq[c0 + cc + e], pq[e]); }
+        }
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+    if (p.ostats && tid < pl.BN && n0 + tid < p.Cout) {
+      double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + n0 + tid) * 2;
+      atomicAdd(st, (double)s_sum[tid]);
+      atomicAdd(st + 1, (double)s_sq[tid]);
+    }
+  } else if (warp == NPW) {
+    // =================== weight loader (bulk-copy engine) ===================
+    if (lane == 0) {
+      const __nv_bfloat16* wsrc = p.wb + (size_t)nt * p.k * pl.kcn * (size_t)(pl.BN * KCH);
+      uint32_t it = 0;
+      for (int sc = 0; sc < pl.nsc; ++sc)
+        for (int j = 0; j < p.k; ++j)
+          for (int kc = 0; kc < nwst; ++kc, ++it) {
+            const uint32_t s = it % NSTAGE;
+            mbar_wait(bar_empty(s), ((it / NSTAGE) & 1u) ^ 1u);
+            mbar_expect_tx(bar_full(s), pl.wstage_bytes);
+            const size_t blk = (size_t)j * pl.kcn + (size_t)sc * nwst + kc;
+            bulk_g2s(w0 + s * pl.wstage_bytes, wsrc + blk * (size_t)(pl.BN * KCH), pl.wstage_bytes, bar_full(s));
+          }
+    }
+  } else {
+    // =================== MMA issuer ===================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_lbo = (uint32_t)pl.SR * 16u, a_sbo = 128u;
+      const uint32_t b_lbo = (uint32_t)pl.BN * 16u, b_sbo = 128u;
+      uint32_t it = 0;
+      for (int sc = 0; sc < pl.nsc; ++sc) {
+        const int b = sc % pl.nslab;
+        mbar_wait(bar_slab_full(b), ((uint32_t)(sc / pl.nslab)) & 1u);
+        tc_fence_after();
+        const uint32_t sbase = slab0 + (uint32_t)b * pl.slab_bytes;
+        for (int j = 0; j < p.k; ++j)
+          for (int kc = 0; kc < nwst; ++kc, ++it) {
+            const uint32_t s = it % NSTAGE;
+            mbar_wait(bar_full(s), (it / NSTAGE) & 1u);
+            tc_fence_after();
+            const uint32_t wbase = w0 + s * pl.wstage_bytes;
+#pragma unroll
+            for (int kk = 0; kk < KCH / 16; ++kk) {
+              const uint32_t aaddr = sbase + (uint32_t)(((kc * 8 + kk * 2) * pl.SR + j * p.dil) * 16);
+              const uint32_t baddr = wbase + (uint32_t)(kk * 2 * pl.BN * 16);
+              const uint64_t ad = make_desc(aaddr, a_lbo, a_sbo);
+              const uint64_t bd = make_desc(baddr, b_lbo, b_sbo);
+              umma_bf16(tmem_base, ad, bd, idesc, (it | (uint32_t)kk) != 0u);
+            }
+            umma_commit(bar_empty(s));          // stage free once these MMAs have read it
+          }
+        umma_commit(bar_slab_empty(b));          // slab free once every MMA issued so far has completed
+      }
+      umma_commit(bar_acc);                      // accumulator complete
+    }
+  }
+  __syncthreads();
+  if (warp == NPW + 1) tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+void pads(int Cin, int Cout, int& cin_pad, int& cout_pad, int& BN) {
+  cin_pad = Cin <= 64 ? 64 : round_up(Cin, 128);
+  if (Cout <= 256) { cout_pad = round_up(Cout, 32); BN = cout_pad; }
+  else { cout_pad = round_up(Cout, 256); BN = 256; }
+}
+
+bool make_plan(const ConvArgs& a, Plan& pl) {
+  int cin_pad, cout_pad, BN;
+  pads(a.Cin, a.Cout, cin_pad, cout_pad, BN);
+  if (cin_pad != a.cin_pad || cout_pad != a.cout_pad) return false;
+  pl.BN = BN;
+  pl.ntile_n = cout_pad / BN;
+  pl.KS = cin_pad < 128 ? cin_pad : 128;
+  pl.nsc = cin_pad / pl.KS;
+  pl.nslab = pl.nsc > 1 ? 2 : 1;
+  pl.kcn = cin_pad / KCH;
+  pl.SR = (BM + (a.k - 1) * a.dil) | 1;
+  int tc = 32;
+  while (tc < BN) tc <<= 1;
+  pl.tmem_cols = tc;
+  uint32_t off = 16;
+  pl.off_bar = off; off += 128;
+  pl.off_stats = off; off += 512 * 4;
+  pl.off_par = off; off += 5u * cin_pad * 4u;
+  off = (off + 127u) & ~127u;
+  pl.off_slab = off;
+  pl.slab_bytes = (uint32_t)(pl.KS / 8) * pl.SR * 16u;
+  pl.slab_bytes = (pl.slab_bytes + 127u) & ~127u;
+  uint32_t slab_total = pl.slab_bytes * pl.nslab;
+  pl.wstage_bytes = (uint32_t)BN * KCH * 2u;
+  uint32_t region = slab_total + NSTAGE * pl.wstage_bytes;
+  if (region < (uint32_t)(NPW * STG_BYTES)) region = NPW * STG_BYTES;      // the epilogue staging tiles alias this region
+  pl.off_w = pl.off_slab + slab_total;
+  pl.smem_bytes = pl.off_slab + region;
+  return pl.smem_bytes <= 227u * 1024u;
+}
+
+}  // namespace
+
+// bf16 image of the weights: [Cout tile][tap][64-channel chunk][8-channel plane][BN rows][8 channels]
+void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, std::vector<__nv_bfloat16>& out, int& cin_pad, int& cout_pad) {
+  int BN;
+  pads(Cin, Cout, cin_pad, cout_pad, BN);
+  const int kcn = cin_pad / KCH, ntn = cout_pad / BN;
+  out.assign((size_t)ntn * k * kcn * BN * KCH, __float2bfloat16(0.f));
+  for (int nt = 0; nt < ntn; ++nt)
+    for (int j = 0; j < k; ++j)
+      for (int kc = 0; kc < kcn; ++kc)
+        for (int pln = 0; pln < 8; ++pln)
+          for (int n = 0; n < BN; ++n) {
+            const int co = nt * BN + n;
+            if (co >= Cout) continue;
+            const size_t base = (((((size_t)nt * k + j) * kcn + kc) * 8 + pln) * BN + n) * 8;
+            for (int e = 0; e < 8; ++e) {
+              const int ci = kc * KCH + pln * 8 + e;
+              if (ci < Cin) out[base + e] = __float2bfloat16(w[((size_t)j * Cin + ci) * ldw + co]);
+            }
+          }
+}
+
+bool conv_umma_supported(const ConvArgs& a) {
+  if (!a.wb || a.stride != 1 || a.act != ACT_NONE) return false;
+  if (a.in_shr != 0 && (a.k != 1 || a.pad != 0)) return false;
+  if ((a.ldx & 3) || (reinterpret_cast<uintptr_t>(a.x) & 15)) return false;
+  if ((a.ldy & 3) || (reinterpret_cast<uintptr_t>(a.y) & 15)) return false;
+  if (a.res && ((a.ldr & 3) || (reinterpret_cast<uintptr_t>(a.res) & 15))) return false;
+  if (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)) return false;
+  if (a.tile_rows != BM) return false;
+  Plan pl;
+  return make_plan(a, pl);
+}
+
+cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
+  if (a.ntiles <= 0) return cudaSuccess;
+  UArgs u;
+  u.a = a;
+  if (!make_plan(a, u.p)) return cudaErrorInvalidValue;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(a.ntiles, u.p.ntile_n);
+  conv_umma_kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
+  return launched();
+}
+
+}  // namespace ttsb
