@@ -1,0 +1,250 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+Protocol and its rationale: tests/parity.py and DESIGN.md "Parity protocol"."""
+import numpy as np
+import pytest
+import torch
+
+import illufly_tts_b200 as pkg
+from illufly_tts_b200.synthetic import ids_to_phonemes, random_ids, synthetic_config, synthetic_voice_pack, vocoder_inputs, workload
+from oracle.kokoro_oracle import make_noise
+from tests.parity import back_half, front_half, oracle_taps_cat, rel_err, snr_db
+
+pytestmark = pytest.mark.gpu
+
+
+def small_batch(lens, speeds=None, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    ids = [random_ids(g, n) for n in lens]
+    pack = synthetic_voice_pack(1)
+    ref = torch.stack([pack[n - 1, 0] for n in lens])
+    return dict(ids=ids, ref_s=ref, speeds=speeds or [1.0] * len(lens))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# whole path
+# ---------------------------------------------------------------------------------------------------------
+def test_single_utterance_fp32(engine, oracle):
+    """BASELINE configs[0]: one short utterance.  ints exact, front taps 1e-4, waveform 1e-3 (fp32)"""
+    engine.set_precision(pkg.PRECISION_FP32)
+    w = workload("single")
+    fh = front_half(engine, oracle, w)
+    rec = back_half(engine, oracle, w, fh, tol_abs=1e-3)
+    assert rec[0]["snr"] > 60
+
+
+def test_ragged_batch_fp32(engine, oracle):
+    """ragged batch with speeds: durations/indices bit-exact incl. the padded-LSTM quirk of forward_batch (App. C-1)"""
+    engine.set_precision(pkg.PRECISION_FP32)
+    w = small_batch([12, 40, 25, 40], [1.0, 0.9, 1.1, 1.25])
+    fh = front_half(engine, oracle, w, padded_lstm=True)
+    back_half(engine, oracle, w, fh, tol_abs=1e-3)
+
+
+def test_single_semantics_differ_from_batched(engine, oracle):
+    """padded_lstm=False gives KModel.forward's per-utterance durations: equal to the oracle run alone"""
+    engine.set_precision(pkg.PRECISION_FP32)
+    w = small_batch([10, 31])
+    alone = [oracle.forward_batch([w["ids"][i]], w["ref_s"][i:i + 1], [1.0], stop_after_durations=True) for i in range(2)]
+    r = engine.synthesize(w["ids"], w["ref_s"], w["speeds"], padded_lstm=False, seed=3)
+    for i in range(2):
+        assert torch.equal(r.pred_dur[i], alone[i].pred_dur[0])
+
+
+def test_bf16_tensor_core_path(engine, oracle):
+    """tcgen05 mode: same integer outputs; waveform SNR >= 40 dB against the oracle on bit-identical generator inputs"""
+    engine.set_precision(pkg.PRECISION_BF16)
+    try:
+        w = small_batch([20, 33])
+        fh = front_half(engine, oracle, w, frame_tol=5e-2)
+        rec = back_half(engine, oracle, w, fh, min_snr=40.0)
+        assert all(r["max_abs"] < 2e-2 for r in rec)
+    finally:
+        engine.set_precision(pkg.PRECISION_FP32)
+
+
+@pytest.mark.parametrize("precision,tol,snr", [(pkg.PRECISION_FP32, 1e-3, 60.0), (pkg.PRECISION_BF16, None, 40.0)])
+def test_vocoder_only(engine, oracle, precision, tol, snr):
+    """BASELINE configs[3] (vocoder sweep), small sizes: generator only on bit-identical inputs"""
+    engine.set_precision(precision)
+    try:
+        for (B, L) in [(1, 100), (3, 40)]:
+            x, s, f0, noise = vocoder_inputs(B, L)
+            engine.enable_taps(True)
+            audio = engine.vocoder(x, s, f0, noise)
+            har = engine.read_tap("har")
+            engine.enable_taps(False)
+            for b in range(B):
+                ph0 = har[b * (60 * L + 1), 11:22][None]
+                ref = oracle.vocoder(x[b:b + 1], s[b:b + 1], f0[b:b + 1], noise[b:b + 1], None, ph0)[0]
+                a = audio[b].cpu()
+                assert a.shape == ref.shape == (300 * L,)
+                if tol is not None:
+                    assert float((a - ref).abs().max()) <= tol
+                assert snr_db(ref, a) >= snr
+    finally:
+        engine.enable_taps(False)
+        engine.set_precision(pkg.PRECISION_FP32)
+
+
+def test_forced_durations_and_in_kernel_noise(engine):
+    """forced durations drive the frame count; Philox noise path: deterministic for a seed, different across seeds"""
+    w = small_batch([9, 14])
+    forced = [[2] * len(x) for x in w["ids"]]
+    r1 = engine.synthesize(w["ids"], w["ref_s"], forced_dur=forced, seed=5, want_indices=True)
+    r2 = engine.synthesize(w["ids"], w["ref_s"], forced_dur=forced, seed=5)
+    r3 = engine.synthesize(w["ids"], w["ref_s"], forced_dur=forced, seed=6)
+    for i, x in enumerate(w["ids"]):
+        assert r1.audio[i].numel() == 600 * 2 * len(x)
+        assert torch.equal(r1.indices[i], torch.repeat_interleave(torch.arange(len(x)), 2))
+        assert torch.isfinite(r1.audio[i]).all()
+        assert float((r1.audio[i] - r2.audio[i]).abs().max()) < 1e-4          # fp32 atomics reorder statistics sums only
+        assert float((r1.audio[i] - r3.audio[i]).abs().max()) > 1e-4
+
+
+def test_edge_lengths(engine, oracle):
+    """shortest (one symbol + BOS/EOS) and longest (512 tokens) utterances; > 512 is refused like kokoro's assert"""
+    engine.set_precision(pkg.PRECISION_FP32)
+    w = small_batch([1, 510], seed=4)
+    o = oracle.forward_batch(w["ids"], w["ref_s"], w["speeds"], stop_after_durations=True)
+    r = engine.synthesize(w["ids"], w["ref_s"], w["speeds"], seed=1, want_indices=True)
+    for i in range(2):
+        assert torch.equal(r.pred_dur[i], o.pred_dur[i])
+        assert torch.equal(r.indices[i], o.indices[i])
+        assert r.audio[i].numel() == 600 * int(o.pred_dur[i].sum()) and torch.isfinite(r.audio[i]).all()
+    with pytest.raises(pkg._lib.EngineError) as ei:
+        engine.synthesize([[0] + [5] * 511 + [0]], w["ref_s"][:1])
+    assert ei.value.code == pkg._lib.E_TOO_LONG
+
+
+def test_batch32_full_size_properties(engine, oracle):
+    """BASELINE configs[1] at full size: durations bit-exact for all 32 utterances (oracle front only: seconds on CPU);
+    size-independent properties of the waveform: length == 600 * sum(dur), finite, bounded, utterance b of the batch equals
+    utterance b synthesised alone with the same durations (batch independence)"""
+    engine.set_precision(pkg.PRECISION_BF16)
+    try:
+        w = workload("batch32")
+        o = oracle.forward_batch(w["ids"], w["ref_s"], w["speeds"], stop_after_durations=True)
+        r = engine.synthesize(w["ids"], w["ref_s"], w["speeds"], seed=9, want_indices=True)
+        flips = 0
+        for i in range(32):
+            if not torch.equal(r.pred_dur[i], o.pred_dur[i]):
+                flips += 1
+            assert torch.equal(r.indices[i], torch.repeat_interleave(torch.arange(len(w["ids"][i])), r.pred_dur[i]))
+            assert r.audio[i].numel() == 600 * int(r.pred_dur[i].sum())
+            assert torch.isfinite(r.audio[i]).all() and float(r.audio[i].abs().max()) < 10.0
+        assert flips == 0, f"{flips} utterances with a duration flip"
+        k = 7
+        noise = [make_noise(0, k, int(r.pred_dur[k].sum()))]
+        full = engine.synthesize(w["ids"], w["ref_s"], w["speeds"], noise=[make_noise(0, i, int(r.pred_dur[i].sum())) for i in range(32)])
+        solo = engine.synthesize([w["ids"][k]], w["ref_s"][k:k + 1], [1.0], noise=noise, forced_dur=[r.pred_dur[k].tolist()])
+        assert snr_db(solo.audio[0].cpu(), full.audio[k].cpu()) > 50
+    finally:
+        engine.set_precision(pkg.PRECISION_FP32)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# drop-in class
+# ---------------------------------------------------------------------------------------------------------
+def test_batchkmodel_surface(checkpoint, oracle):
+    m = pkg.BatchKModel(repo_id=None, config=synthetic_config(), model=checkpoint, strict=True).to("cuda:0").eval()
+    assert m.device.type == "cuda" and isinstance(m.vocab, dict)
+    w = small_batch([12, 12])
+    ph = [ids_to_phonemes(x) for x in w["ids"]]
+    out = m.forward_batch(ph, w["ref_s"].unsqueeze(1), [1.0, 1.0])                # pipeline.py:607
+    assert isinstance(out, list) and len(out) == 2 and all(o.is_cuda and o.dim() == 1 and o.dtype == torch.float32 for o in out)
+    o = oracle.forward_batch(w["ids"], w["ref_s"], [1.0, 1.0], stop_after_durations=True)
+    assert [a.numel() for a in out] == [600 * int(p.sum()) for p in o.pred_dur]
+    res = m(ph[0], w["ref_s"][:1], 1.0, return_output=True)                       # pipeline.py:204-206
+    assert res.audio.device.type == "cpu" and res.pred_dur.dtype == torch.int64
+    alone = oracle.forward_batch(w["ids"][:1], w["ref_s"][:1], [1.0], stop_after_durations=True)
+    assert torch.equal(res.pred_dur, alone.pred_dur[0])
+    with pytest.raises(ValueError):                                               # strict mode raises instead of silence
+        m.forward_batch(["abc", ph[0]], w["ref_s"].unsqueeze(1))
+    compat = pkg.BatchKModel(config=synthetic_config(), model=checkpoint).to("cuda:0")
+    short = compat.forward_batch(["abc", ph[0]], w["ref_s"].unsqueeze(1))
+    assert len(short) == 1 and short[0].shape == (24000,)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# single kernels
+# ---------------------------------------------------------------------------------------------------------
+def test_op_istft_matches_torch(engine):
+    g = torch.Generator().manual_seed(0)
+    Fs = [3, 17, 1]
+    rows = [120 * f + 1 for f in Fs]
+    cp = torch.randn(sum(rows), 24, generator=g) * 0.7
+    audio = engine.op_istft(cp.cuda(), Fs).cpu()
+    win = torch.hann_window(20, periodic=True)
+    o, a0 = 0, 0
+    for f, n in zip(Fs, rows):
+        x = cp[o:o + n, :22].t()[None]
+        spec, ph = torch.exp(x[:, :11]), torch.sin(x[:, 11:])
+        ref = torch.istft(spec * torch.exp(ph * 1j), 20, 5, 20, window=win)[0]
+        got = audio[a0:a0 + 600 * f]
+        assert got.shape == ref.shape
+        assert float((got - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+        o += n
+        a0 += 600 * f
+
+
+def test_op_adain_snake_matches_torch(engine):
+    g = torch.Generator().manual_seed(1)
+    lens, C = [700, 33, 256], 128
+    off = np.concatenate([[0], np.cumsum(lens)])
+    x = torch.randn(sum(lens), C, generator=g) * 2 + 0.5
+    gb = torch.randn(len(lens), 2 * C, generator=g) * 0.3
+    alpha = torch.rand(C, generator=g) + 0.5
+    y = engine.op_adain_snake(x.cuda(), off, gb.cuda(), alpha.cuda()).cpu()
+    for b, n in enumerate(lens):
+        xb = x[off[b]:off[b + 1]].t()[None]
+        v = (1 + gb[b, :C, None]) * torch.nn.functional.instance_norm(xb, eps=1e-5) + gb[b, C:, None]
+        ref = (v + (1 / alpha[:, None]) * torch.sin(alpha[:, None] * v) ** 2)[0].t()
+        assert float((y[off[b]:off[b + 1]] - ref).abs().max()) < 2e-5
+
+
+def test_op_length_regulate_is_exact(engine):
+    g = torch.Generator().manual_seed(2)
+    lens = [5, 64, 1, 200]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    dur = torch.randint(1, 12, (sum(lens),), generator=g, dtype=torch.int32)
+    src = torch.randn(sum(lens), 640, generator=g)
+    idx, dst, f_off = engine.op_length_regulate(dur.cuda(), off, src.cuda(), int(dur.sum()))
+    idx, dst = idx.cpu(), dst.cpu()
+    for b, n in enumerate(lens):
+        d = dur[off[b]:off[b + 1]].long()
+        ref_idx = torch.repeat_interleave(torch.arange(n), d)
+        assert f_off[b + 1] - f_off[b] == int(d.sum())
+        assert torch.equal(idx[f_off[b]:f_off[b + 1]].long(), ref_idx)
+        assert torch.equal(dst[f_off[b]:f_off[b + 1]], src[off[b]:off[b + 1]][ref_idx])      # a gather: bit-exact
+
+
+@pytest.mark.parametrize("Cin,Cout,k,d", [(128, 128, 3, 1), (128, 128, 11, 5), (256, 256, 7, 3), (512, 2560, 1, 1), (640, 1024, 3, 1), (128, 24, 7, 1)])
+def test_op_conv1d_both_kernels(engine, Cin, Cout, k, d):
+    g = torch.Generator().manual_seed(3)
+    lens = [300, 77, 129]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    x = torch.randn(sum(lens), Cin, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+
+    def ref(xx, ww):
+        outs = [torch.nn.functional.conv1d(xx[off[i]:off[i + 1]].t()[None], ww, b, dilation=d, padding=(k * d - d) // 2)[0].t() for i in range(len(lens))]
+        return torch.cat(outs, 0)
+    y32 = engine.op_conv1d(x.cuda(), w, b, off, d, pkg.PRECISION_FP32).cpu()
+    assert float((y32 - ref(x, w)).abs().max()) < 5e-5
+    y16 = engine.op_conv1d(x.cuda(), w, b, off, d, pkg.PRECISION_BF16).cpu()
+    assert float((y16 - ref(x.bfloat16().float(), w.bfloat16().float())).abs().max()) < 5e-5      # exact products, fp32 accumulate
+    assert float((y16 - ref(x, w)).abs().max()) < 5e-2
+
+
+def test_op_bilstm_matches_torch(engine):
+    torch.manual_seed(4)
+    lstm = torch.nn.LSTM(640, 256, 1, batch_first=True, bidirectional=True)
+    lens = [17, 1, 130]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    x = torch.randn(sum(lens), 640)
+    y = engine.op_bilstm(x.cuda(), lstm.state_dict(), off).cpu()
+    with torch.no_grad():
+        for i, n in enumerate(lens):
+            ref, _ = lstm(x[off[i]:off[i + 1]][None])
+            assert float((y[off[i]:off[i + 1]] - ref[0]).abs().max()) < 2e-5

@@ -1,0 +1,145 @@
+"""CPU tests (-m "not gpu") of the host side: the C-ABI library loads and exports every symbol the header declares, the
+BatchKModel mirror keeps the reference's surface and error behaviour, partitioning, and the N>1 sharding over gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import illufly_tts_b200 as pkg
+from illufly_tts_b200 import _lib
+from illufly_tts_b200.kmodel import phonemes_to_ids
+from illufly_tts_b200.synthetic import ids_to_phonemes, synthetic_checkpoint, synthetic_config, synthetic_vocab, workload
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    header = open(os.path.join(ROOT, "include", "ttsb200.h")).read()
+    declared = set(re.findall(r"TTSB_API\s+[\w\s\*]+?\b(ttsb_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()                      # dlopen works without a GPU; no compute call is made here
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ttsb_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (ttsb_\w+)", out))
+    assert exported == declared
+
+
+def test_engine_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.EngineError) as ei:
+        pkg.Engine(synthetic_checkpoint(1234), 0)
+    assert "no CUDA device" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_no_cpu_device():
+    m = pkg.BatchKModel(config=synthetic_config(), model={k: {} for k in ("bert", "bert_encoder", "predictor", "decoder", "text_encoder")})
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.to("cpu")
+    with pytest.raises(RuntimeError, match="call .to"):
+        m.engine
+
+
+def test_phonemes_to_ids_matches_reference_mapping():
+    vocab = synthetic_vocab()
+    assert len(vocab) == 177 and min(vocab.values()) == 1 and max(vocab.values()) == 177
+    s = "ab世c"                     # unknown character dropped (kmodel.py:38-39), BOS/EOS = 0 (kmodel.py:41)
+    assert phonemes_to_ids(vocab, s) == [0, vocab["a"], vocab["b"], vocab["c"], 0]
+    ids = workload("single")["ids"][0]
+    assert phonemes_to_ids(vocab, ids_to_phonemes(ids)) == ids
+
+
+def test_forward_batch_error_surface_without_engine():
+    """kmodel.py:27-30: any phoneme string shorter than 5 -> ONE-element list of zeros(24000), before any compute;
+    kmodel.py:147-150: any failure -> B x zeros(24000)"""
+    m = pkg.BatchKModel(config=synthetic_config(), model={k: {} for k in ("bert", "bert_encoder", "predictor", "decoder", "text_encoder")})
+    out = m.forward_batch(["abcdefgh", "abc"], torch.zeros(2, 1, 256))
+    assert len(out) == 1 and out[0].shape == (24000,) and float(out[0].abs().sum()) == 0.0
+    out = m.forward_batch(["abcdefgh", "abcdefg"], torch.zeros(2, 1, 256))          # no engine -> exception -> silence per item
+    assert len(out) == 2 and all(o.shape == (24000,) for o in out)
+    strict = pkg.BatchKModel(config=synthetic_config(), model={k: {} for k in ("bert", "bert_encoder", "predictor", "decoder", "text_encoder")}, strict=True)
+    with pytest.raises(ValueError):
+        strict.forward_batch(["abc"], torch.zeros(1, 1, 256))
+    with pytest.raises(RuntimeError):
+        strict.forward_batch(["abcdefgh"], torch.zeros(1, 1, 256))
+
+
+def test_install_into_reference_module_slot():
+    mod = pkg.install_into_reference()
+    assert sys.modules["illufly_tts.core.kmodel"].BatchKModel is pkg.BatchKModel
+    assert mod.BatchKModel is pkg.BatchKModel
+    del sys.modules["illufly_tts.core.kmodel"]
+
+
+def test_checkpoint_manifest_matches_generator(checkpoint):
+    from illufly_tts_b200.synthetic import manifest
+    man = manifest()
+    for mod, sd in checkpoint.items():
+        assert {k[7:] for k in sd} == set(man[mod])
+        for k, v in sd.items():
+            assert list(v.shape) == man[mod][k[7:]], (mod, k)
+    ck2 = synthetic_checkpoint(1234)
+    assert torch.equal(ck2["decoder"]["module.generator.ups.1.weight_v"], checkpoint["decoder"]["module.generator.ups.1.weight_v"])
+
+
+def test_lpt_partition_and_micro_batches():
+    costs = [5, 9, 2, 7, 7, 1, 3, 8]
+    parts = pkg.lpt_partition(costs, 3)
+    assert sorted(i for p in parts for i in p) == list(range(8))
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= max(costs)
+    assert pkg.lpt_partition(costs, 3) == parts                     # deterministic
+    assert pkg.lpt_partition([], 2) == [[], []]
+    mbs = pkg.micro_batches(costs, 10)
+    assert sorted(i for p in mbs for i in p) == list(range(8))
+    assert all(sum(costs[i] for i in p) <= 10 or len(p) == 1 for p in mbs)
+    assert pkg.micro_batches([50], 10) == [[0]]
+
+
+def test_world_size_2_sharding_gloo(tmp_path):
+    """the N>1 path: ranks partition the utterances (no collective on the data path), then max-over-ranks time and summed
+    units are reduced exactly as bench.py does — exercised with gloo on CPU, world_size 2"""
+    script = tmp_path / "w.py"
+    script.write_text(f'''
+import os, sys, json
+sys.path.insert(0, {ROOT!r})
+import torch, torch.distributed as dist
+import illufly_tts_b200 as pkg
+from illufly_tts_b200.synthetic import workload
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+w = workload("fleet64")
+costs = [len(x) for x in w["ids"]]
+mine = pkg.lpt_partition(costs, world)[rank]
+t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+units = torch.tensor([float(sum(costs[i] for i in mine)), float(len(mine))], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+dist.all_reduce(units, op=dist.ReduceOp.SUM)
+if rank == 0:
+    print(json.dumps(dict(tmax=t.item(), tokens=units[0].item(), n=units[1].item(), want=float(sum(costs)))))
+dist.barrier()
+dist.destroy_process_group()
+''')
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29613",
+                        str(script)], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["tmax"] == 2.0 and d["n"] == 64 and d["tokens"] == d["want"]
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """--impl reference is the CPU oracle arm: must print one JSON line without a GPU"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-utts", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0

@@ -1,0 +1,119 @@
+"""CPU tests of the oracle itself (-m "not gpu"): structure pinned to the published Kokoro-82M numbers, the ALBERT
+restatement pinned to transformers.AlbertModel, geometry, and the two ill-conditioned points the parity protocol works around."""
+import math
+
+import pytest
+import torch
+
+from oracle.kokoro_oracle import Albert, KokoroConfig, make_noise
+from oracle.synth_weights import vocoder_inputs, workload
+
+
+def test_param_counts(oracle):
+    """per-module parameter split of Kokoro-82M (bert 6.29 M, bert_encoder 0.39 M, predictor 16.20 M,
+    text_encoder 5.60 M, decoder 53.29 M; total 81.78 M)"""
+    def n(m):
+        return sum(p.numel() for k, p in m.state_dict().items() if ".norm.weight" not in k and ".norm.bias" not in k)
+    got = {k: n(getattr(oracle, k)) for k in ("bert", "bert_encoder", "predictor", "text_encoder", "decoder")}
+    # published split (rounded): 6.29 / 0.39 / 16.2 / 5.6 / 53.3 M, "Kokoro-82M"; bert == transformers.AlbertModel exactly
+    assert got["bert"] == 6_292_480
+    assert got["bert_encoder"] == 393_728
+    assert abs(got["predictor"] / 1e6 - 16.20) < 0.01
+    assert abs(got["text_encoder"] / 1e6 - 5.60) < 0.01
+    assert abs(got["decoder"] / 1e6 - 53.29) < 0.02
+    assert sum(got.values()) == 81_763_410
+
+
+def test_checkpoint_layout(checkpoint):
+    """the real checkpoint layout: five state dicts, module.-prefixed keys, old-style weight_g / weight_v"""
+    assert set(checkpoint) == {"bert", "bert_encoder", "predictor", "decoder", "text_encoder"}
+    for sd in checkpoint.values():
+        assert all(k.startswith("module.") for k in sd)
+    dec = checkpoint["decoder"]
+    assert dec["module.generator.ups.0.weight_v"].shape == (512, 256, 20)
+    assert dec["module.generator.ups.0.weight_g"].shape == (512, 1, 1)
+    assert dec["module.generator.conv_post.weight_v"].shape == (22, 128, 7)
+    assert "module.generator.resblocks.5.alpha2.2" in dec
+    assert checkpoint["predictor"]["module.text_encoder.lstms.1.fc.weight"].shape == (1024, 128)
+
+
+def test_albert_matches_transformers():
+    """the ~60-line ALBERT restatement against the independent implementation kokoro actually uses"""
+    transformers = pytest.importorskip("transformers")
+    c = KokoroConfig()
+    cfg = transformers.AlbertConfig(vocab_size=c.n_token, embedding_size=128, hidden_size=768, num_attention_heads=12, intermediate_size=2048,
+                                    max_position_embeddings=512, num_hidden_layers=12, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    torch.manual_seed(0)
+    ref = transformers.AlbertModel(cfg).eval()
+    mine = Albert(c).eval()
+    missing, unexpected = mine.load_state_dict(ref.state_dict(), strict=False)
+    assert not [k for k in missing if "position_ids" not in k], missing
+    ids = torch.randint(1, 178, (3, 37))
+    ids[1, 30:] = 0
+    am = torch.ones_like(ids)
+    am[1, 30:] = 0
+    with torch.no_grad():
+        a = ref(ids, attention_mask=am).last_hidden_state
+        b = mine(ids, am)
+    valid = am.bool()
+    assert float((a - b)[valid].abs().max()) < 2e-5
+
+
+def test_geometry(oracle):
+    """audio length == 600 * sum(pred_dur); STFT frames == 120 F + 1; indices == repeat_interleave"""
+    w = workload("single")
+    o = oracle.forward_batch(w["ids"], w["ref_s"], w["speeds"], want_taps=True)
+    F = int(o.pred_dur[0].sum())
+    assert o.audio[0].numel() == 600 * F
+    assert o.taps[0]["har"].shape == (1, 22, 120 * F + 1)
+    assert o.taps[0]["gen_in"].shape == (1, 512, 2 * F)
+    assert torch.equal(o.indices[0], torch.repeat_interleave(torch.arange(len(w["ids"][0])), o.pred_dur[0]))
+    assert int(o.pred_dur[0].min()) >= 1
+
+
+def test_round_half_even_and_clamp(oracle):
+    d = torch.tensor([0.2, 0.5, 1.5, 2.5, 3.49, 3.51])
+    assert torch.round(d).clamp(min=1).long().tolist() == [1, 1, 2, 2, 3, 4]
+
+
+def test_padded_lstm_quirk_changes_short_utterances(oracle):
+    """App. C-1: in forward_batch the duration LSTM runs over the zero-padded batch, so a short utterance batched with a
+    long one sees different (pre-round) durations than alone"""
+    w = workload("batch32")
+    ids = [w["ids"][0][:20] + [0], w["ids"][1]]
+    ref = w["ref_s"][:2]
+    both = oracle.forward_batch(ids, ref, [1.0, 1.0], stop_after_durations=True)
+    alone = oracle.forward_batch(ids[:1], ref[:1], [1.0], stop_after_durations=True)
+    assert float((both.duration[0] - alone.duration[0]).abs().max()) > 1e-4
+
+
+def test_reference_is_chaotic_in_f0(oracle):
+    """the reference cannot be reproduced to 1e-3 across fp32 summation orders: a 1e-6 relative perturbation of F0 moves
+    the oracle's own waveform by far more than 1e-3 (phase integrates F0)"""
+    w = workload("single")
+    o = oracle.forward_batch(w["ids"], w["ref_s"], w["speeds"], want_taps=True)
+    t = o.taps[0]
+    F = int(o.pred_dur[0].sum())
+    nz = make_noise(0, 0, F)[None]
+    s = w["ref_s"][:, :128]
+    g = torch.Generator().manual_seed(0)
+    f0 = t["F0"][None]
+    a0 = oracle.vocoder(t["gen_in"], s, f0, nz)
+    a1 = oracle.vocoder(t["gen_in"], s, f0 * (1 + 1e-6 * torch.randn(f0.shape, generator=g)), nz)
+    assert float((a0 - a1).abs().max()) > 1e-3
+
+
+def test_stft_frame0_phase_is_rounding_noise(oracle):
+    """frame 0 of the centre-padded STFT is symmetric: Im X_k is ~1e-9 noise, so angle() is 0 or +-pi by its sign"""
+    x, s, f0, noise = vocoder_inputs(1, 20)
+    gen = oracle.decoder.generator
+    har = gen.m_source(f0, noise)
+    z = torch.stft(har, 20, 5, 20, window=gen.window, return_complex=True)
+    assert float(z[0, :, 0].imag.abs().max()) < 1e-6 * float(z[0, :, 0].real.abs().max()) + 1e-7
+    assert float(z[0, :, 1].imag.abs().max()) > 1e-4
+
+
+def test_noise_is_reproducible():
+    assert torch.equal(make_noise(0, 3, 5), make_noise(0, 3, 5))
+    assert make_noise(0, 3, 5).shape == (3000, 9)
+    assert math.isclose(float(make_noise(1, 0, 50).std()), 1.0, rel_tol=0.02)
