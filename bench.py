@@ -139,7 +139,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TTSB_BENCH_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("TTSB_BENCH_PRECISION", "f16"), choices=["f16", "bf16", "fp32"])
     ap.add_argument("--ref-utts", type=int, default=2, help="utterances per step of the CPU reference arm")
     ap.add_argument("--cpu-baseline-utts", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -159,7 +159,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3)
-    prec = pkg.PRECISION_BF16 if args.precision == "bf16" else pkg.PRECISION_FP32
+    prec = {"f16": pkg.PRECISION_FP16, "bf16": pkg.PRECISION_BF16, "fp32": pkg.PRECISION_FP32}[args.precision]
 
     ckpt = synthetic_checkpoint(1234)                                   # random-init weights of the Kokoro-82M architecture
     model = pkg.BatchKModel(config=synthetic_config(), model=ckpt, precision=prec, strict=True).to(f"cuda:{local}").eval()
@@ -239,7 +239,7 @@ def main():
                 hbm[k] = dict(achieved_gbs=g, frac=g / peaks["hbm"], ms_per_step=q["ms"] / args.steps)
         line = dict(metric=METRIC, value=audio_total * args.steps / (dev_ms_max * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=warmup,
                     ms_per_step=dev_ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
-                    dtype="bf16" if prec == pkg.PRECISION_BF16 else "f32", data="synthetic",
+                    dtype={"f16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision], data="synthetic",
                     config=dict(workload="configs[1]: batch of 32 short utterances (60-90 symbols each), one voice, per GPU", utterances_per_gpu=len(tokens),
                                 tokens_per_gpu=sum(tokens), frames_per_gpu=sum(frames), audio_s_per_step_per_gpu=audio_s, weights="seeded random init, Kokoro-82M architecture",
                                 partitioning="utterances by rank, no collective", l2="inputs larger than L2: every stage buffer of a step exceeds 126 MB",

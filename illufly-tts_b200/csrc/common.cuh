@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace ttsb {
@@ -34,7 +35,8 @@ enum Act : int { ACT_NONE = 0, ACT_GELU_NEW = 1, ACT_LRELU = 2 };
 struct ConvArgs {
   const float* x; int ldx;
   const float* w; int ldw;             // [k][Cin][ldw], ldw = Cout rounded up to 4
-  const __nv_bfloat16* wb;             // tensor-core path: [k][CoutPad][CinPad] bf16 (K-major), else null
+  const uint16_t* wb;                  // tensor-core path: 16-bit operand image of the weights (conv_umma.cu), else null
+  int wfmt;                            // operand format of wb and of the activation slab: 0 = bf16, 1 = fp16
   int cin_pad, cout_pad;
   const float* bias;
   float* y; int ldy;
@@ -128,6 +130,6 @@ __device__ __forceinline__ void adain_coef(const double* st, int n, float gamma,
 #include <vector>
 namespace ttsb {
 // host: repack fp32 [k][Cin][ldw] weights into the bf16 shared-memory image the tcgen05 kernel streams (conv_umma.cu)
-void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, std::vector<__nv_bfloat16>& out, int& cin_pad, int& cout_pad);
+void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fmt, std::vector<uint16_t>& out, int& cin_pad, int& cout_pad);
 const char* last_error();
 }  // namespace ttsb

@@ -119,6 +119,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);     // saturate instead of producing inf
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
@@ -218,7 +224,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           }
         }
         uint4 o;
-        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+        if (p.wfmt == 1) { o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]); }
+        else { o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]); }
         *reinterpret_cast<uint4*>(slab + (size_t)r * 16) = o;
       }
       fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   } else if (warp == NPW) {
     // =================== weight loader (bulk-copy engine) ===================
     if (lane == 0) {
-      const __nv_bfloat16* wsrc = p.wb + (size_t)nt * p.k * pl.kcn * (size_t)(pl.BN * KCH);
+      const uint16_t* wsrc = p.wb + (size_t)nt * p.k * pl.kcn * (size_t)(pl.BN * KCH);
       uint32_t it = 0;
       for (int sc = 0; sc < pl.nsc; ++sc)
         for (int j = 0; j < p.k; ++j)
@@ -317,7 +324,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   } else {
     // =================== MMA issuer ===================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pl.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t ofmt = p.wfmt == 1 ? 0u : 1u;     // instruction-descriptor operand format: 0 = F16, 1 = BF16
+      const uint32_t idesc = (1u << 4) | (ofmt << 7) | (ofmt << 10) | ((uint32_t)(pl.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_lbo = (uint32_t)pl.SR * 16u, a_sbo = 128u;
       const uint32_t b_lbo = (uint32_t)pl.BN * 16u, b_sbo = 128u;
       uint32_t it = 0;
@@ -392,12 +400,12 @@ bool make_plan(const ConvArgs& a, Plan& pl) {
 
 }  // namespace
 
-// bf16 image of the weights: [Cout tile][tap][64-channel chunk][8-channel plane][BN rows][8 channels]
-void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, std::vector<__nv_bfloat16>& out, int& cin_pad, int& cout_pad) {
+// 16-bit (bf16 or fp16) image of the weights: [Cout tile][tap][64-channel chunk][8-channel plane][BN rows][8 channels]
+void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fmt, std::vector<uint16_t>& out, int& cin_pad, int& cout_pad) {
   int BN;
   pads(Cin, Cout, cin_pad, cout_pad, BN);
   const int kcn = cin_pad / KCH, ntn = cout_pad / BN;
-  out.assign((size_t)ntn * k * kcn * BN * KCH, __float2bfloat16(0.f));
+  out.assign((size_t)ntn * k * kcn * BN * KCH, (uint16_t)0);
   for (int nt = 0; nt < ntn; ++nt)
     for (int j = 0; j < k; ++j)
       for (int kc = 0; kc < kcn; ++kc)
@@ -408,7 +416,11 @@ void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, std::v
             const size_t base = (((((size_t)nt * k + j) * kcn + kc) * 8 + pln) * BN + n) * 8;
             for (int e = 0; e < 8; ++e) {
               const int ci = kc * KCH + pln * 8 + e;
-              if (ci < Cin) out[base + e] = __float2bfloat16(w[((size_t)j * Cin + ci) * ldw + co]);
+              if (ci < Cin) {
+                const float v = w[((size_t)j * Cin + ci) * ldw + co];
+                if (fmt == 1) { const __half hv = __float2half(v); out[base + e] = *reinterpret_cast<const uint16_t*>(&hv); }
+                else { const __nv_bfloat16 bv = __float2bfloat16(v); out[base + e] = *reinterpret_cast<const uint16_t*>(&bv); }
+              }
             }
           }
 }

@@ -167,9 +167,11 @@ void Loader::pack_conv(const HostTensor& w, const std::vector<float>* bias, Conv
   c.w = upload(p);
   c.bias = bias ? upload(*bias) : nullptr;
   if (want_bf16) {
-    std::vector<__nv_bfloat16> pb;
-    pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, pb, c.cin_pad, c.cout_pad);
+    std::vector<uint16_t> pb;
+    pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, 0, pb, c.cin_pad, c.cout_pad);
     c.wb = upload(pb);
+    pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, 1, pb, c.cin_pad, c.cout_pad);
+    c.wh = upload(pb);
   }
 }
 
@@ -449,7 +451,9 @@ struct ConvCall {
 int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = c.x; a.ldx = c.ldx; a.w = c.w->w; a.ldw = c.w->ldw; a.wb = c.w->wb; a.cin_pad = c.w->cin_pad; a.cout_pad = c.w->cout_pad;
+  const bool f16 = r.e.precision == TTSB_PRECISION_FP16;
+  a.x = c.x; a.ldx = c.ldx; a.w = c.w->w; a.ldw = c.w->ldw; a.wb = f16 ? c.w->wh : c.w->wb; a.wfmt = f16 ? 1 : 0;
+  a.cin_pad = c.w->cin_pad; a.cout_pad = c.w->cout_pad;
   a.bias = c.w->bias; a.y = c.y; a.ldy = c.ldy; a.res = c.res; a.ldr = c.ldr;
   a.Cin = c.w->Cin; a.Cout = c.w->Cout; a.k = c.w->k; a.dil = c.dil; a.pad = c.pad; a.stride = c.stride; a.in_shr = c.in_shr;
   a.pro = c.pro; a.slope = c.slope;
@@ -463,7 +467,7 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   const double rows = (double)t.out_rows;
   const double fl = 2.0 * rows * a.Cin * a.Cout * a.k;
   const double by = 4.0 * rows * ((double)a.Cout * (1 + (a.res ? 1 : 0) + (a.accumulate ? 1 : 0))) + 4.0 * (double)t.in_rows * a.Cin;
-  if (c.tensor && r.e.precision == TTSB_PRECISION_BF16 && conv_umma_supported(a)) {
+  if (c.tensor && r.e.precision != TTSB_PRECISION_FP32 && conv_umma_supported(a)) {
     r.e.prof.begin(r.s, PROF_CONV_TENSOR, fl, by);
     CK(launch_conv_umma(a, r.s));
   } else {

@@ -19,7 +19,8 @@ struct HostTensor {
 struct ConvW {
   float* w = nullptr; int ldw = 0;        // fp32 [k][Cin][ldw]
   float* bias = nullptr;                  // [Cout] or null
-  __nv_bfloat16* wb = nullptr;            // bf16 UMMA pack (see conv_umma.cu), or null
+  uint16_t* wb = nullptr;                 // bf16 UMMA pack (see conv_umma.cu), or null
+  uint16_t* wh = nullptr;                 // fp16 UMMA pack, or null
   int cin_pad = 0, cout_pad = 0;
   int Cin = 0, Cout = 0, k = 1;
 };

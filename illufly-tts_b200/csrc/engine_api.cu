@@ -144,7 +144,7 @@ int ttsb_engine_finalize(ttsb_engine* h) {
 }
 
 int ttsb_engine_set_precision(ttsb_engine* h, int precision) {
-  if (!h || (precision != TTSB_PRECISION_FP32 && precision != TTSB_PRECISION_BF16)) { set_error("set_precision: bad arguments"); return TTSB_E_INVALID; }
+  if (!h || (precision != TTSB_PRECISION_FP32 && precision != TTSB_PRECISION_BF16 && precision != TTSB_PRECISION_FP16)) { set_error("set_precision: bad arguments"); return TTSB_E_INVALID; }
   h->e.precision = precision;
   return TTSB_OK;
 }
@@ -327,23 +327,24 @@ int ttsb_op_conv1d(ttsb_engine* h, const float* x, const float* w, const float* 
   for (int co = 0; co < Cout; ++co)
     for (int ci = 0; ci < Cin; ++ci)
       for (int j = 0; j < k; ++j) p[((size_t)j * Cin + ci) * ldw + co] = w[((size_t)co * Cin + ci) * k + j];
-  std::vector<__nv_bfloat16> pb;
+  std::vector<uint16_t> pb;
   int cin_pad = 0, cout_pad = 0;
-  pack_umma_weights(p.data(), k, Cin, Cout, ldw, pb, cin_pad, cout_pad);
+  const int wfmt = precision == TTSB_PRECISION_FP16 ? 1 : 0;
+  pack_umma_weights(p.data(), k, Cin, Cout, ldw, wfmt, pb, cin_pad, cout_pad);
   float* dw = (float*)e.arena.alloc(sizeof(float) * p.size());
-  __nv_bfloat16* dwb = (__nv_bfloat16*)e.arena.alloc(sizeof(__nv_bfloat16) * std::max<size_t>(pb.size(), 8));
+  uint16_t* dwb = (uint16_t*)e.arena.alloc(sizeof(uint16_t) * std::max<size_t>(pb.size(), 8));
   float* db = bias ? (float*)e.arena.alloc(sizeof(float) * Cout) : nullptr;
   if (!dw || !dwb || (bias && !db)) { set_error("workspace allocation failed"); return TTSB_E_NOMEM; }
   CKA(cudaMemcpyAsync(dw, p.data(), sizeof(float) * p.size(), cudaMemcpyHostToDevice, e.stream));
-  if (!pb.empty()) CKA(cudaMemcpyAsync(dwb, pb.data(), sizeof(__nv_bfloat16) * pb.size(), cudaMemcpyHostToDevice, e.stream));
+  if (!pb.empty()) CKA(cudaMemcpyAsync(dwb, pb.data(), sizeof(uint16_t) * pb.size(), cudaMemcpyHostToDevice, e.stream));
   if (bias) CKA(cudaMemcpyAsync(db, bias, sizeof(float) * Cout, cudaMemcpyHostToDevice, e.stream));
   CKA(cudaStreamSynchronize(e.stream));
   ConvArgs a;
   memset(&a, 0, sizeof(a));
-  a.x = x; a.ldx = Cin; a.w = dw; a.ldw = ldw; a.wb = pb.empty() ? nullptr : dwb; a.cin_pad = cin_pad; a.cout_pad = cout_pad; a.bias = db;
+  a.x = x; a.ldx = Cin; a.w = dw; a.ldw = ldw; a.wb = pb.empty() ? nullptr : dwb; a.wfmt = wfmt; a.cin_pad = cin_pad; a.cout_pad = cout_pad; a.bias = db;
   a.y = y; a.ldy = Cout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.dil = dilation; a.pad = (k * dilation - dilation) / 2; a.stride = 1;
   a.out_scale = 1.f; a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
-  const bool tensor = precision == TTSB_PRECISION_BF16;
+  const bool tensor = precision != TTSB_PRECISION_FP32;
   if (tensor && !conv_umma_supported(a)) { set_error("op_conv1d: shape not supported by the tcgen05 kernel"); return TTSB_E_INVALID; }
   if (reps < 1) reps = 1;
   OpTimer tm(e, ms);

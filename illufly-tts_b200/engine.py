@@ -16,6 +16,7 @@ from . import _lib
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+PRECISION_FP16 = 2
 CHECKPOINT_MODULES = ("bert", "bert_encoder", "predictor", "decoder", "text_encoder")
 
 

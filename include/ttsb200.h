@@ -47,7 +47,9 @@ enum {
  * durations, always runs in fp32. */
 enum {
   TTSB_PRECISION_FP32 = 0,   /* CUDA-core fp32 everywhere: waveform within 1e-3 max-abs of the fp32 reference   */
-  TTSB_PRECISION_BF16 = 1    /* tcgen05 bf16 operands, fp32 accumulate/statistics: >= 40 dB SNR                 */
+  TTSB_PRECISION_BF16 = 1,   /* tcgen05 (kind::f16) bf16 operands, fp32 accumulate/statistics                    */
+  TTSB_PRECISION_FP16 = 2    /* tcgen05 (kind::f16) fp16 operands (saturating), fp32 accumulate/statistics: same
+                                instruction and rate as bf16, 3 more mantissa bits (~ +18 dB SNR)                */
 };
 
 enum {

@@ -103,7 +103,7 @@ def main():
     t = time.time()
     o = m.forward_batch(w["ids"], w["ref_s"], w["speeds"], noise_seed=0, want_taps=True)
     print(f"oracle: {time.time() - t:.2f}s  frames={[int(p.sum()) for p in o.pred_dur]}")
-    eng = pkg.Engine(m.export_checkpoint(), 0, pkg.PRECISION_BF16 if prec == "bf16" else pkg.PRECISION_FP32)
+    eng = pkg.Engine(m.export_checkpoint(), 0, {"fp32": pkg.PRECISION_FP32, "bf16": pkg.PRECISION_BF16, "f16": pkg.PRECISION_FP16}[prec])
     eng.enable_taps(True)
     B = len(w["ids"])
     # durations first (no noise needed), then the full run with the oracle's noise

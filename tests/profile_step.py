@@ -10,7 +10,7 @@ import torch  # noqa: E402
 import illufly_tts_b200 as pkg  # noqa: E402
 from illufly_tts_b200.synthetic import synthetic_checkpoint, workload  # noqa: E402
 
-prec = pkg.PRECISION_FP32 if (len(sys.argv) > 1 and sys.argv[1] == "fp32") else pkg.PRECISION_BF16
+prec = {"fp32": pkg.PRECISION_FP32, "bf16": pkg.PRECISION_BF16, "f16": pkg.PRECISION_FP16}[sys.argv[1] if len(sys.argv) > 1 else "f16"]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 eng = pkg.Engine(synthetic_checkpoint(1234), 0, prec)
 w = workload("batch32")
