@@ -19,7 +19,6 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const ConvArgs p) {
   extern __shared__ float dyn[];            // [3][CinR]: mean, a, b  (+ alpha, 1/alpha when snake) -> 5*CinR
   __shared__ __align__(16) float As[2][BK][LDA];
   __shared__ __align__(16) float Bs[2][BK][BN];
-  __shared__ float csum[BN], csq[BN];
 
   const Tile tile = p.tiles[blockIdx.x];
   const Seg seg = p.segs[tile.seg];
@@ -43,7 +42,6 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const ConvArgs p) {
       if (p.pro == PRO_ADAIN_SNAKE) { float al = p.alpha[c]; s_al[c] = al; s_ial[c] = 1.0f / al; }
     }
   }
-  if (tid < BN) { csum[tid] = 0.f; csq[tid] = 0.f; }
   __syncthreads();
 
   const int kchunks = (p.Cin + BK - 1) / BK;
@@ -193,19 +191,27 @@ __global__ void __launch_bounds__(NT) conv_simt_kernel(const ConvArgs p) {
     }
   }
   if (p.ostats) {
+    // deterministic in-CTA reduction: every thread parks its partials (the operand tiles are dead by now), then one
+    // thread per channel adds the 16 row-groups in a fixed order; the cross-CTA sum is a double atomic (order changes
+    // it by ~1e-16 relative, below fp32 resolution of the statistics)
+    float* part_s = &As[0][0][0];     // [16][BN]
+    float* part_q = &Bs[0][0][0];     // [16][BN]
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int cl = h * 64 + tx * 4 + e;
-        atomicAdd(&csum[cl], ps[h * 4 + e]);
-        atomicAdd(&csq[cl], pq[h * 4 + e]);
+        part_s[ty * BN + cl] = ps[h * 4 + e];
+        part_q[ty * BN + cl] = pq[h * 4 + e];
       }
     __syncthreads();
     if (tid < BN && n0 + tid < p.Cout) {
+      float s = 0.f, q = 0.f;
+#pragma unroll
+      for (int g = 0; g < 16; ++g) { s += part_s[g * BN + tid]; q += part_q[g * BN + tid]; }
       double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + n0 + tid) * 2;
-      atomicAdd(st, (double)csum[tid]);
-      atomicAdd(st + 1, (double)csq[tid]);
+      atomicAdd(st, (double)s);
+      atomicAdd(st + 1, (double)q);
     }
   }
 }

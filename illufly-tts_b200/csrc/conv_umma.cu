@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   auto bar_slab_full = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
   auto bar_slab_empty = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
   const uint32_t bar_acc = bar0 + 8u * (2 * NSTAGE + 4);
-  float* s_sum = reinterpret_cast<float*>(smem + pl.off_stats);
-  float* s_sq = s_sum + 256;
+  float* s_sum = reinterpret_cast<float*>(smem + pl.off_stats);     // [4 row quadrants][256]
+  float* s_sq = s_sum + 4 * 256;
   float* s_par = reinterpret_cast<float*>(smem + pl.off_par);     // [5][cin_pad]: mean, a, b, alpha, 1/alpha
   const int cpad = p.cin_pad;
 
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       s_par[c] = mean; s_par[cpad + c] = a; s_par[2 * cpad + c] = b; s_par[3 * cpad + c] = al; s_par[4 * cpad + c] = 1.0f / al;
     }
   }
-  for (int c = tid; c < 512; c += NTHREADS) s_sum[c] = 0.f;
+  for (int c = tid; c < 2048; c += NTHREADS) s_sum[c] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -293,9 +293,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);  pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 8);
           ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16); pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 16);
         }
-        if (lane < 8) {
+        if (lane < 8) {          // one writer per (row quadrant, channel): plain stores, fixed-order sum below => deterministic
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { atomicAdd(&s_sum[c0 + cc + e], ps[e]); atomicAdd(&s_sq[c0 + cc + e], pq[e]); }
+          for (int e = 0; e < 4; ++e) { s_sum[q * 256 + c0 + cc + e] = ps[e]; s_sq[q * 256 + c0 + cc + e] = pq[e]; }
         }
       }
     }
@@ -303,8 +303,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
     if (p.ostats && tid < pl.BN && n0 + tid < p.Cout) {
       double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + n0 + tid) * 2;
-      atomicAdd(st, (double)s_sum[tid]);
-      atomicAdd(st + 1, (double)s_sq[tid]);
+      const float ts = (s_sum[tid] + s_sum[256 + tid]) + (s_sum[512 + tid] + s_sum[768 + tid]);
+      const float tq = (s_sq[tid] + s_sq[256 + tid]) + (s_sq[512 + tid] + s_sq[768 + tid]);
+      atomicAdd(st, (double)ts);
+      atomicAdd(st + 1, (double)tq);
     }
   } else if (warp == NPW) {
     // =================== weight loader (bulk-copy engine) ===================
@@ -383,7 +385,7 @@ bool make_plan(const ConvArgs& a, Plan& pl) {
   pl.tmem_cols = tc;
   uint32_t off = 16;
   pl.off_bar = off; off += 128;
-  pl.off_stats = off; off += 512 * 4;
+  pl.off_stats = off; off += 2048 * 4;
   pl.off_par = off; off += 5u * cin_pad * 4u;
   off = (off + 127u) & ~127u;
   pl.off_slab = off;
