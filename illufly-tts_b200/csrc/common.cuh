@@ -55,6 +55,12 @@ struct LstmSeg {
   int off, len, pre;                   // rows; `pre` = zero-input steps the REVERSE direction runs first (padded-batch quirk)
 };
 
+// a group of utterances whose recurrences one cluster runs together (lstm_cluster.cu); len 0 = empty slot
+constexpr int LSTM_UB = 4;
+struct LstmGroup {
+  int off[LSTM_UB], len[LSTM_UB], pre[LSTM_UB];
+};
+
 #define TTSB_CHECK_LAUNCH() do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return e__; } while (0)
 
 // number of kernels launched by this library (bench.py reports it as gpu_launches)
@@ -68,6 +74,8 @@ bool conv_umma_supported(const ConvArgs& a);
 
 cudaError_t launch_lstm(const float* gx, const float* whhT, const float* bias, float* y, int ldy,
                         const LstmSeg* segs, int nseg, cudaStream_t s);
+cudaError_t launch_lstm_cluster(const float* gx, const float* whh, const float* bias, float* y, int ldy, const LstmGroup* groups, int ngroups,
+                                cudaStream_t s);
 cudaError_t launch_attention(const float* qkv, float* ctx, const Seg* segs, int nseg, int max_len, int heads, cudaStream_t s);
 cudaError_t launch_albert_embed(const int* ids, const int* pos, const float* word, const float* posw, const float* type0,
                                 const float* g, const float* b, float* out, int rows, cudaStream_t s);

@@ -15,7 +15,7 @@ constexpr int LDA = BM + 4;
 
 struct __align__(16) F4 { float v[4]; };
 
-__global__ void __launch_bounds__(NT) conv_simt_kernel(const ConvArgs p) {
+__global__ void __launch_bounds__(NT, 2) conv_simt_kernel(const ConvArgs p) {
   extern __shared__ float dyn[];            // [3][CinR]: mean, a, b  (+ alpha, 1/alpha when snake) -> 5*CinR
   __shared__ __align__(16) float As[2][BK][LDA];
   __shared__ __align__(16) float Bs[2][BK][BN];

@@ -198,6 +198,9 @@ bool Loader::lstm(const std::string& prefix, LstmW& l) {
     for (int g = 0; g < 1024; ++g)
       for (int kk = 0; kk < 256; ++kk) t[((size_t)d * 256 + kk) * 1024 + g] = whh[d]->data[(size_t)g * 256 + kk];
   l.whhT = upload(t);
+  std::vector<float> o((size_t)2 * 1024 * 256);
+  for (int d = 0; d < 2; ++d) memcpy(&o[(size_t)d * 1024 * 256], whh[d]->data.data(), sizeof(float) * 1024 * 256);
+  l.whh = upload(o);
   return true;
 }
 
@@ -478,12 +481,27 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   return TTSB_OK;
 }
 
+// utterances sorted by step count and dealt LSTM_UB at a time to the clusters of lstm_cluster_kernel
+std::vector<LstmGroup> make_lstm_groups(const std::vector<LstmSeg>& segs) {
+  std::vector<int> order(segs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return segs[a].len + segs[a].pre > segs[b].len + segs[b].pre; });
+  std::vector<LstmGroup> g((segs.size() + LSTM_UB - 1) / LSTM_UB);
+  for (auto& x : g) memset(&x, 0, sizeof(x));
+  for (size_t i = 0; i < order.size(); ++i) {
+    LstmGroup& x = g[i / LSTM_UB];
+    const LstmSeg& sg = segs[order[i]];
+    x.off[i % LSTM_UB] = sg.off; x.len[i % LSTM_UB] = sg.len; x.pre[i % LSTM_UB] = sg.pre;
+  }
+  return g;
+}
+
 // x W_ih -> gates, then the recurrence
-int run_bilstm(Run& r, const LstmW& l, const float* x, int ldx, float* gx, float* y, int ldy, const SegTab& t, const LstmSeg* lsegs) {
+int run_bilstm(Run& r, const LstmW& l, const float* x, int ldx, float* gx, float* y, int ldy, const SegTab& t, const LstmGroup* groups, int ngroups) {
   ConvCall c; c.w = &l.ih; c.x = x; c.ldx = ldx; c.y = gx; c.ldy = 2048;
   RC(run_conv(r, c, t));
   r.e.prof.begin(r.s, PROF_LSTM, 2.0 * t.out_rows * 2 * 1024 * 256, 0.0);
-  CK(launch_lstm(gx, l.whhT, l.ih.bias, y, ldy, lsegs, t.nseg, r.s));
+  CK(launch_lstm_cluster(gx, l.whh, l.ih.bias, y, ldy, groups, ngroups, r.s));
   r.e.prof.end(r.s);
   return TTSB_OK;
 }
@@ -684,7 +702,7 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
     if (ids[token_offsets[0] + i] < 0 || ids[token_offsets[0] + i] >= 178) { set_error("begin: token id out of range at %d", i); return TTSB_E_INVALID; }
 
   // ---- tables + inputs, one upload ----
-  RC(r.tables_begin((size_t)B * (sizeof(Seg) + 2 * sizeof(LstmSeg) + 260 * sizeof(float)) + (size_t)(R / 128 + B + 8) * sizeof(Tile) + (size_t)R * 16 + 8192));
+  RC(r.tables_begin((size_t)B * (sizeof(Seg) + 2 * sizeof(LstmGroup) + 260 * sizeof(float)) + (size_t)(R / 128 + B + 8) * sizeof(Tile) + (size_t)R * 16 + 8192));
   e.tabT = r.make_tab(e.spT, e.spT);
   std::vector<int> h_ids(ids + token_offsets[0], ids + token_offsets[0] + R), h_pos(R), h_r2s(R);
   std::vector<LstmSeg> ls(B), lsq(B);
@@ -698,8 +716,10 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   const int* d_ids = r.push(h_ids);
   const int* d_pos = r.push(h_pos);
   const int* d_r2s = r.push(h_r2s);
-  const LstmSeg* d_ls = r.push(ls);
-  const LstmSeg* d_lsq = r.push(lsq);
+  const std::vector<LstmGroup> g_ls = make_lstm_groups(ls), g_lsq = make_lstm_groups(lsq);
+  const LstmGroup* d_ls = r.push(g_ls);
+  const LstmGroup* d_lsq = r.push(g_lsq);
+  const int n_ls = (int)g_ls.size();
   const float* d_speed = r.push(h_speed);
   const float* d_ref = r.push(h_ref);
   std::vector<int> h_forced;
@@ -745,7 +765,7 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   CK(launch_fill_style(d_ref, 256, 128, d_r2s, X, 640, 512, 128, R, r.s));
   RC(r.tap("d_en", X, R, 512, 640));
   for (int l = 0; l < 3; ++l) {
-    RC(run_bilstm(r, e.de_lstm[l], X, 640, GX, Y, 512, tT, d_ls));
+    RC(run_bilstm(r, e.de_lstm[l], X, 640, GX, Y, 512, tT, d_ls, n_ls));
     CK(launch_layernorm(Y, 512, nullptr, 0, X, 640, R, 512, 1e-5f, 1, nullptr, nullptr, e.d_gbP + e.de_aln[l].off, ldP, d_r2s, ACT_NONE, 0.f, r.s));
   }
   RC(r.tap("d", X, R, 640, 640));
@@ -758,7 +778,7 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   int* d_cum = r.alloc<int>(R);
   int* d_tot = r.alloc<int>(B);
   if (!logits || !d_dur || !d_pd || !d_cum || !d_tot) return TTSB_E_NOMEM;
-  RC(run_bilstm(r, e.dur_lstm, X, 640, GX, Y, 512, tT, d_lsq));
+  RC(run_bilstm(r, e.dur_lstm, X, 640, GX, Y, 512, tT, d_lsq, n_ls));
   { ConvCall c; c.w = &e.dur_proj; c.x = Y; c.ldx = 512; c.y = logits; c.ldy = 52; RC(run_conv(r, c, tT)); }
   CK(launch_duration(logits, 52, 50, d_r2s, d_speed, d_dur, d_pd, R, r.s));
   const int* d_used = d_forced ? d_forced : d_pd;
@@ -782,7 +802,7 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
     RC(run_conv(r, c, tT));
     CK(launch_layernorm(TE1, 512, nullptr, 0, TE0, 512, R, 512, 1e-5f, 0, e.te_ln_g[l], e.te_ln_b[l], nullptr, 0, nullptr, ACT_LRELU, 0.2f, r.s));
   }
-  RC(run_bilstm(r, e.te_lstm, TE0, 512, GX, TEN, 512, tT, d_ls));
+  RC(run_bilstm(r, e.te_lstm, TE0, 512, GX, TEN, 512, tT, d_ls, n_ls));
   RC(r.tap("t_en", TEN, R, 512, 512));
   e.d_ten = TEN;
 
@@ -813,7 +833,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   Space spL; spL.build(lL);
   const int RL = spL.total;
 
-  RC(r.tables_begin((size_t)B * 8 * sizeof(Seg) + (size_t)(RL / 128 + 4 * B + 16) * 4 * sizeof(Tile) + (size_t)RF * 4 + (size_t)B * sizeof(LstmSeg) + 8192));
+  RC(r.tables_begin((size_t)B * 8 * sizeof(Seg) + (size_t)(RL / 128 + 4 * B + 16) * 4 * sizeof(Tile) + (size_t)RF * 4 + (size_t)B * sizeof(LstmGroup) + 8192));
   const SegTab tTF = r.make_tab(spT, spF, 1, 1, false);
   const SegTab tF = r.make_tab(spF, spF);
   const SegTab tL = r.make_tab(spL, spL);
@@ -826,7 +846,8 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
     lsF[b] = {spF.off[b], spF.len[b], 0};
   }
   const int* d_f2s = r.push(f2s);
-  const LstmSeg* d_lsF = r.push(lsF);
+  const std::vector<LstmGroup> g_lsF = make_lstm_groups(lsF);
+  const LstmGroup* d_lsF = r.push(g_lsF);
   RC(r.tables_upload());
   RC(r.stats_begin(B, 40960));
 
@@ -867,7 +888,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   float* F0 = r.alloc<float>(RL);
   float* NN = r.alloc<float>(RL);
   if (!GX || !SH || !st_sh || !F0 || !NN) return TTSB_E_NOMEM;
-  RC(run_bilstm(r, e.shared_lstm, EN, 640, GX, SH, 512, tF, d_lsF));
+  RC(run_bilstm(r, e.shared_lstm, EN, 640, GX, SH, 512, tF, d_lsF, (int)g_lsF.size()));
   CK(launch_colstats(SH, 512, 512, tF.segs, B, st_sh, 512, r.s));
   for (int br = 0; br < 2; ++br) {
     const ResBlk1dW* blk = br == 0 ? e.f0_blk : e.n_blk;

@@ -376,18 +376,20 @@ int ttsb_op_bilstm(ttsb_engine* h, const float* x, int In, const float* w_ih, co
   for (int d = 0; d < 2; ++d)
     for (int g = 0; g < 1024; ++g)
       for (int kk = 0; kk < 256; ++kk) whhT[((size_t)d * 256 + kk) * 1024 + g] = w_hh[((size_t)d * 1024 + g) * 256 + kk];
-  std::vector<LstmSeg> ls(B);
-  for (int b = 0, o = 0; b < B; ++b) { ls[b] = {o, l[b], 0}; o += l[b]; }
+  std::vector<LstmGroup> ls((B + LSTM_UB - 1) / LSTM_UB);
+  for (auto& g : ls) memset(&g, 0, sizeof(g));
+  for (int b = 0, o = 0; b < B; ++b) { ls[b / LSTM_UB].off[b % LSTM_UB] = o; ls[b / LSTM_UB].len[b % LSTM_UB] = l[b]; o += l[b]; }
+  std::vector<float> whh_o(w_hh, w_hh + (size_t)2 * 1024 * 256);
   float* dw = (float*)e.arena.alloc(sizeof(float) * p.size());
   float* db = (float*)e.arena.alloc(sizeof(float) * 2048);
-  float* dh = (float*)e.arena.alloc(sizeof(float) * whhT.size());
+  float* dh = (float*)e.arena.alloc(sizeof(float) * whh_o.size());
   float* gx = (float*)e.arena.alloc(sizeof(float) * (size_t)t.total * 2048);
-  LstmSeg* dls = (LstmSeg*)e.arena.alloc(sizeof(LstmSeg) * B);
+  LstmGroup* dls = (LstmGroup*)e.arena.alloc(sizeof(LstmGroup) * ls.size());
   if (!dw || !db || !dh || !gx || !dls) { set_error("workspace allocation failed"); return TTSB_E_NOMEM; }
   CKA(cudaMemcpyAsync(dw, p.data(), sizeof(float) * p.size(), cudaMemcpyHostToDevice, e.stream));
   CKA(cudaMemcpyAsync(db, bias.data(), sizeof(float) * 2048, cudaMemcpyHostToDevice, e.stream));
-  CKA(cudaMemcpyAsync(dh, whhT.data(), sizeof(float) * whhT.size(), cudaMemcpyHostToDevice, e.stream));
-  CKA(cudaMemcpyAsync(dls, ls.data(), sizeof(LstmSeg) * B, cudaMemcpyHostToDevice, e.stream));
+  CKA(cudaMemcpyAsync(dh, whh_o.data(), sizeof(float) * whh_o.size(), cudaMemcpyHostToDevice, e.stream));
+  CKA(cudaMemcpyAsync(dls, ls.data(), sizeof(LstmGroup) * ls.size(), cudaMemcpyHostToDevice, e.stream));
   CKA(cudaStreamSynchronize(e.stream));
   ConvArgs a;
   memset(&a, 0, sizeof(a));
@@ -396,7 +398,7 @@ int ttsb_op_bilstm(ttsb_engine* h, const float* x, int In, const float* w_ih, co
   OpTimer tm(e, ms);
   CKA(tm.start());
   CKA(launch_conv_simt(a, e.stream));
-  CKA(launch_lstm(gx, dh, db, y, 512, dls, B, e.stream));
+  CKA(launch_lstm_cluster(gx, dh, db, y, 512, dls, (int)ls.size(), e.stream));
   CKA(tm.stop());
   CKA(cudaStreamSynchronize(e.stream));
   return TTSB_OK;

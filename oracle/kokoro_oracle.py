@@ -431,16 +431,19 @@ class Generator(nn.Module):
     def istft(self, mag, phase):
         return torch.istft(mag * torch.exp(phase * 1j), self.n_fft, self.hop, self.n_fft, window=self.window)
 
-    def forward(self, x, s, f0, noise, taps=None, frame0_phase=None):
+    def forward(self, x, s, f0, noise, taps=None, har_override=None):
         har_source = self.m_source(f0, noise)
         mag, ang = self.stft(har_source)
-        if frame0_phase is not None:
-            # STFT frame 0 is exactly symmetric (reflect padding about sample 0), so Im X_k(0) is pure rounding noise and
-            # angle() is +-pi by the SIGN of that noise wherever Re < 0: FFT-library dependent, not a property of the model.
-            # Parity runs pin those 11 values to the implementation under test (tests/, DESIGN.md "ill-conditioned points").
-            ang = ang.clone()
-            ang[:, :, 0] = frame0_phase
         har = torch.cat([mag, ang], dim=1)
+        if taps is not None:
+            taps["har_own"] = har
+        if har_override is not None:
+            # angle() is discontinuous: wherever Im X ~ 0 and Re X < 0 it is +pi or -pi by the SIGN of rounding noise (always at
+            # STFT frame 0, which reflect padding makes exactly symmetric, and wherever a bin crosses the negative real axis).
+            # That sign depends on the FFT library, not on the model.  Parity runs therefore (1) compare the implementation's
+            # source spectrum with this one as COMPLEX numbers and (2) feed the implementation's [mag | angle] features here,
+            # so the rest of the generator is compared on bit-identical inputs (tests/parity.py).
+            har = har_override
         if taps is not None:
             taps["har_source"], taps["har"] = har_source, har
         for i in range(self.nu):
@@ -479,7 +482,7 @@ class Decoder(nn.Module):
         self.asr_res = nn.Sequential(weight_norm(nn.Conv1d(512, 64, 1)))
         self.generator = Generator(c)
 
-    def forward(self, asr, F0_curve, N, s, noise, taps=None, frame0_phase=None):
+    def forward(self, asr, F0_curve, N, s, noise, taps=None, har_override=None):
         F0 = self.F0_conv(F0_curve[:, None])
         Nn = self.N_conv(N[:, None])
         x = self.encode(torch.cat([asr, F0, Nn], dim=1), s)
@@ -493,7 +496,7 @@ class Decoder(nn.Module):
                 res = False
         if taps is not None:
             taps["gen_in"] = x
-        return self.generator(x, s, F0_curve, noise, taps, frame0_phase)
+        return self.generator(x, s, F0_curve, noise, taps, har_override)
 
 
 # --------------------------------------------------------------------------------------
@@ -601,9 +604,9 @@ class KokoroOracle(nn.Module):
         return out
 
     @torch.no_grad()
-    def vocoder(self, x, s, f0, noise, taps=None, frame0_phase=None):
+    def vocoder(self, x, s, f0, noise, taps=None, har_override=None):
         """Generator only (BASELINE config 4): x [B,512,L], s [B,128], f0 [B,L], noise [B,300L,9]."""
-        return self.decoder.generator(x, s, f0, noise, taps, frame0_phase).squeeze(1)
+        return self.decoder.generator(x, s, f0, noise, taps, har_override).squeeze(1)
 
 
 def make_noise(seed: int, utt: int, frames: int) -> torch.Tensor:

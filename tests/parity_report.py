@@ -81,10 +81,10 @@ def vocoder_report(m, eng, o, w):
         # oracle with the degenerate STFT frame 0 pinned to the engine's phases
         L = 2 * Fs[i]
         t2 = {}
-        b2 = m.vocoder(x[i:i + 1, :, :L], s[i:i + 1], f0[i:i + 1, :L], nz[i:i + 1, :300 * L], t2, har_e[row, 11:22][None])[0]
+        b2 = m.vocoder(x[i:i + 1, :, :L], s[i:i + 1], f0[i:i + 1, :L], nz[i:i + 1, :300 * L], t2, har_e[row:row + 60 * L + 1].t()[None].contiguous())[0]
         err = a - b2
         prof = [f"{err[k * len(err) // 8:(k + 1) * len(err) // 8].abs().max().item():.1e}" for k in range(8)]
-        print(f"   vs oracle with frame-0 phase pinned: max-abs {err.abs().max().item():.3e} profile {prof}")
+        print(f"   vs oracle fed the engine source spectrum: max-abs {err.abs().max().item():.3e} profile {prof}")
         nrow = 60 * L + 1
         for key in ["gen_stage0", "gen_stage1", "conv_post"]:
             aa = eng.read_tap(key)
