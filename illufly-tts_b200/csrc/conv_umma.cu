@@ -1,4 +1,7 @@
 // tcgen05 implicit-GEMM 1-D convolution over ragged channels-last rows (sm_100a only).
+// Persistent and warp-specialised: one CTA per SM walks a contiguous range of (Cout tile, 128-row tile) work items; producer
+// warps build the operand slab of item i+1 while the tensor core works on item i and the epilogue warps drain item i-1
+// (two slabs, 3-4 weight stages, two TMEM accumulators).
 //
 //   D[time (M = 128 TMEM lanes), Cout tile (N <= 256 TMEM columns)] += A[time + tap*dil - pad, Cin chunk] * W[tap][Cin chunk][Cout]
 //
@@ -24,15 +27,16 @@ constexpr int BM = 128;
 constexpr int KCH = 64;                 // channels per weight stage
 constexpr int NPW = 8;                  // producer / epilogue warps
 constexpr int NPROD = NPW * 32;
-constexpr int NTHREADS = NPROD + 64;    // + weight-loader warp (8) + MMA warp (9)
-constexpr int NSTAGE = 3;
+constexpr int NEPI = 128;               // 4 epilogue warps (one per TMEM lane quadrant)
+constexpr int NTHREADS = NPROD + 64 + NEPI;   // producers (0-7), weight loader (8), MMA issuer (9), epilogue (10-13)
+constexpr int MAXSTAGE = 4;
 constexpr int STG_LD = 36;              // floats per staging row (32 + 4 pad: 16-B aligned rows, conflict-free both ways)
 constexpr int STG_BYTES = 32 * STG_LD * 4;
 constexpr uint32_t SPIN_LIMIT = 40u * 1000u * 1000u;
 
 struct Plan {
-  int BN, KS, nsc, nslab, SR, kcn, tmem_cols, ntile_n;
-  uint32_t off_bar, off_stats, off_par, off_slab, slab_bytes, off_w, wstage_bytes, smem_bytes;
+  int BN, KS, nsc, SR, kcn, tmem_cols, ntile_n, nstage, items, per_cta;
+  uint32_t off_bar, off_stats, off_par, off_stg, off_slab, slab_bytes, off_w, wstage_bytes, smem_bytes;
 };
 
 struct UArgs {
@@ -132,230 +136,319 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   const ConvArgs& p = u.a;
   const Plan& pl = u.p;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Tile tile = p.tiles[blockIdx.x];
-  const Seg seg = p.segs[tile.seg];
-  const int nt = blockIdx.y;
-  const int n0 = nt * pl.BN;
+  const int NS = pl.nstage;
 
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
   const uint32_t bar0 = smem_u32(smem + pl.off_bar);
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (NSTAGE + s); };
-  auto bar_slab_full = [&](int b) { return bar0 + 8u * (2 * NSTAGE + b); };
-  auto bar_slab_empty = [&](int b) { return bar0 + 8u * (2 * NSTAGE + 2 + b); };
-  const uint32_t bar_acc = bar0 + 8u * (2 * NSTAGE + 4);
-  float* s_sum = reinterpret_cast<float*>(smem + pl.off_stats);     // [4 row quadrants][256]
-  float* s_sq = s_sum + 4 * 256;
-  float* s_par = reinterpret_cast<float*>(smem + pl.off_par);     // [5][cin_pad]: mean, a, b, alpha, 1/alpha
+  auto bar_empty = [&](int s) { return bar0 + 8u * (MAXSTAGE + s); };
+  auto bar_slab_full = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + b); };
+  auto bar_slab_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 2 + b); };
+  auto bar_acc_full = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 4 + b); };
+  auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 6 + b); };
+  double* s_sum = reinterpret_cast<double*>(smem + pl.off_stats);   // [4 row quadrants][256], double: the running sums
+  double* s_sq = s_sum + 4 * 256;                                   // must not depend on how tiles are dealt to CTAs
+  float* s_par = reinterpret_cast<float*>(smem + pl.off_par);       // [5][cin_pad]: mean, a, b, alpha, 1/alpha
   const int cpad = p.cin_pad;
+
+  // this CTA's contiguous range of work items; item -> (Cout tile nt, row tile)
+  const int item0 = blockIdx.x * pl.per_cta;
+  const int item1 = min(item0 + pl.per_cta, pl.items);
 
   // ---- one-time setup ----
   if (warp == NPW + 1) tmem_alloc(smem_u32(s_tmem), (uint32_t)pl.tmem_cols);
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(bar_slab_full(b), NPROD); mbar_init(bar_slab_empty(b), 1); }
-    mbar_init(bar_acc, 1);
+    for (int s = 0; s < MAXSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_slab_full(b), NPROD); mbar_init(bar_slab_empty(b), 1);
+      mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), NEPI);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (p.pro >= PRO_ADAIN_LRELU) {
-    for (int c = tid; c < cpad; c += NTHREADS) {
-      float mean = 0.f, a = 0.f, b = 0.f, al = 1.f;
-      if (c < p.Cin) {
-        const double* st = p.pstats + ((size_t)tile.seg * p.ld_pstats + c) * 2;
-        adain_coef(st, seg.in_len, p.gb[(size_t)tile.seg * p.ld_gb + c], p.gb[(size_t)tile.seg * p.ld_gb + p.beta_off + c], mean, a, b);
-        if (p.pro == PRO_ADAIN_SNAKE) al = p.alpha[c];
-      }
-      s_par[c] = mean; s_par[cpad + c] = a; s_par[2 * cpad + c] = b; s_par[3 * cpad + c] = al; s_par[4 * cpad + c] = 1.0f / al;
-    }
-  }
-  for (int c = tid; c < 2048; c += NTHREADS) s_sum[c] = 0.f;
+  for (int c = tid; c < 2048; c += NTHREADS) s_sum[c] = 0.0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  const int nwst = KCH * 0 + pl.KS / KCH;            // weight stages per (slab, tap)
+  const int nwst = pl.KS / KCH;                      // weight stages per (slab, tap)
   const uint32_t slab0 = smem_u32(smem + pl.off_slab);
   const uint32_t w0 = smem_u32(smem + pl.off_w);
 
   if (warp < NPW) {
-    // =================== producers: build the bf16 operand slabs ===================
+    // =================== producers: build the 16-bit operand slabs ===================
     const int planes = pl.KS >> 3;
     const int rpp = NPROD / planes;                    // rows per pass
     const int pln = tid % planes, r0 = tid / planes;
-    for (int sc = 0; sc < pl.nsc; ++sc) {
-      const int b = sc % pl.nslab;
-      mbar_wait(bar_slab_empty(b), (((uint32_t)(sc / pl.nslab)) & 1u) ^ 1u);
-      const int c0 = sc * pl.KS + pln * 8;
-      float pm[8], pa[8], pb[8], pal[8], pia[8];
-      if (p.pro >= PRO_ADAIN_LRELU) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          pm[e] = s_par[c0 + e]; pa[e] = s_par[cpad + c0 + e]; pb[e] = s_par[2 * cpad + c0 + e];
-          pal[e] = s_par[3 * cpad + c0 + e]; pia[e] = s_par[4 * cpad + c0 + e];
-        }
-      }
-      uint8_t* slab = smem + pl.off_slab + (size_t)b * pl.slab_bytes + (size_t)pln * pl.SR * 16;
-      for (int r = r0; r < pl.SR; r += rpp) {
-        const int tin = (tile.t0 + r - p.pad) >> p.in_shr;
-        float v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        const bool valid = (tile.t0 + r - p.pad) >= 0 && tin < seg.in_len && c0 < p.Cin;
-        if (valid) {
-          const float* src = p.x + (size_t)(seg.in_off + tin) * p.ldx + c0;
-          const float4 q0 = *reinterpret_cast<const float4*>(src);
-          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
-          if (c0 + 4 < p.ldx) {
-            const float4 q1 = *reinterpret_cast<const float4*>(src + 4);
-            v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    int cur_seg = -1;
+    uint32_t g = 0;                                    // running slab counter of this CTA
+    for (int item = item0; item < item1; ++item) {
+      const Tile tile = p.tiles[item % p.ntiles];
+      const Seg seg = p.segs[tile.seg];
+      if (p.pro >= PRO_ADAIN_LRELU && tile.seg != cur_seg) {
+        // per-(utterance, channel) AdaIN coefficients; only producers read them, so a producer-only barrier suffices
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+        for (int c = tid; c < cpad; c += NPROD) {
+          float mean = 0.f, a = 0.f, b = 0.f, al = 1.f;
+          if (c < p.Cin) {
+            const double* st = p.pstats + ((size_t)tile.seg * p.ld_pstats + c) * 2;
+            adain_coef(st, seg.in_len, p.gb[(size_t)tile.seg * p.ld_gb + c], p.gb[(size_t)tile.seg * p.ld_gb + p.beta_off + c], mean, a, b);
+            if (p.pro == PRO_ADAIN_SNAKE) al = p.alpha[c];
           }
+          s_par[c] = mean; s_par[cpad + c] = a; s_par[2 * cpad + c] = b; s_par[3 * cpad + c] = al; s_par[4 * cpad + c] = 1.0f / al;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+        cur_seg = tile.seg;
+      }
+      for (int sc = 0; sc < pl.nsc; ++sc, ++g) {
+        const uint32_t b = g & 1u;
+        mbar_wait(bar_slab_empty(b), ((g >> 1) & 1u) ^ 1u);
+        const int c0 = sc * pl.KS + pln * 8;
+        float pm[8], pa[8], pb[8], pal[8], pia[8];
+        if (p.pro >= PRO_ADAIN_LRELU) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float x = v[e];
-            if (p.pro == PRO_LRELU) x = lrelu(x, p.slope);
-            else if (p.pro == PRO_ADAIN_LRELU) x = lrelu(fmaf(x - pm[e], pa[e], pb[e]), p.slope);
-            else if (p.pro == PRO_ADAIN_SNAKE) {
-              const float w = fmaf(x - pm[e], pa[e], pb[e]);
-              const float sn = __sinf(pal[e] * w);
-              x = fmaf(pia[e], sn * sn, w);
-            }
-            v[e] = (c0 + e < p.Cin) ? x : 0.f;
+            pm[e] = s_par[c0 + e]; pa[e] = s_par[cpad + c0 + e]; pb[e] = s_par[2 * cpad + c0 + e];
+            pal[e] = s_par[3 * cpad + c0 + e]; pia[e] = s_par[4 * cpad + c0 + e];
           }
         }
-        uint4 o;
-        if (p.wfmt == 1) { o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]); }
-        else { o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]); }
-        *reinterpret_cast<uint4*>(slab + (size_t)r * 16) = o;
-      }
-      fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
-      mbar_arrive(bar_slab_full(b));
-    }
-
-    // =================== epilogue ===================
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const int q = warp & 3, h = warp >> 2;
-    float* stg = reinterpret_cast<float*>(smem + pl.off_slab + (size_t)warp * STG_BYTES);   // aliases slab 0 (all MMAs are done)
-    const int nchunk = pl.BN >> 5;
-    for (int chunk = h; chunk < nchunk; chunk += 2) {
-      const int c0 = chunk * 32;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        uint8_t* slab = smem + pl.off_slab + (size_t)b * pl.slab_bytes + (size_t)pln * pl.SR * 16;
+        const bool second = c0 + 4 < p.ldx;
+        // two rows per iteration: four 16-B loads in flight per thread before any arithmetic
+        for (int r = r0; r < pl.SR; r += 2 * rpp) {
+          float v[2][8];
+          bool ok[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 f;
-        f.x = __uint_as_float(v[4 * i]); f.y = __uint_as_float(v[4 * i + 1]); f.z = __uint_as_float(v[4 * i + 2]); f.w = __uint_as_float(v[4 * i + 3]);
-        *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * i) = f;
-      }
-      __syncwarp();
-      float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
-      const int cc = (lane & 7) * 4;
-      const int co = n0 + c0 + cc;
+          for (int h = 0; h < 2; ++h) {
+            const int rr = r + h * rpp;
+            const int traw = tile.t0 + rr - p.pad;
+            const int tin = traw >> p.in_shr;
+            ok[h] = rr < pl.SR && traw >= 0 && tin < seg.in_len && c0 < p.Cin;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = 4 * i + (lane >> 3);
-        const int t = tile.t0 + q * 32 + rr;
-        if (t < seg.out_len && co < p.Cout) {
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
-          float x[4] = {a4.x, a4.y, a4.z, a4.w};
-          const size_t orow = (size_t)(seg.out_off + t);
-          float* dst = p.y + orow * p.ldy + co;
-          if (co + 3 < p.Cout) {
-            if (p.bias) { const float4 b4 = *reinterpret_cast<const float4*>(p.bias + co); x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w; }
-            if (p.res) { const float4 r4 = *reinterpret_cast<const float4*>(p.res + orow * p.ldr + co); x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w; }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) x[e] *= p.out_scale;
-            if (p.accumulate) { const float4 y4 = *reinterpret_cast<const float4*>(dst); x[0] += y4.x; x[1] += y4.y; x[2] += y4.z; x[3] += y4.w; }
-            *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (co + e < p.Cout) {
-                float xv = x[e];
-                if (p.bias) xv += p.bias[co + e];
-                if (p.res) xv += p.res[orow * p.ldr + co + e];
-                xv *= p.out_scale;
-                if (p.accumulate) xv += dst[e];
-                dst[e] = xv;
-                x[e] = xv;
-              } else x[e] = 0.f;
+            for (int e = 0; e < 8; ++e) v[h][e] = 0.f;
+            if (ok[h]) {
+              const float* src = p.x + (size_t)(seg.in_off + tin) * p.ldx + c0;
+              const float4 q0 = __ldg(reinterpret_cast<const float4*>(src));
+              v[h][0] = q0.x; v[h][1] = q0.y; v[h][2] = q0.z; v[h][3] = q0.w;
+              if (second) {
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+                v[h][4] = q1.x; v[h][5] = q1.y; v[h][6] = q1.z; v[h][7] = q1.w;
+              }
             }
           }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { ps[e] += x[e]; pq[e] += x[e] * x[e]; }
-        }
-      }
-      __syncwarp();
-      if (p.ostats) {
+          for (int h = 0; h < 2; ++h) {
+            const int rr = r + h * rpp;
+            if (rr >= pl.SR) break;
+            if (ok[h]) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);  pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 8);
-          ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16); pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 16);
+              for (int e = 0; e < 8; ++e) {
+                float x = v[h][e];
+                if (p.pro == PRO_LRELU) x = lrelu(x, p.slope);
+                else if (p.pro == PRO_ADAIN_LRELU) x = lrelu(fmaf(x - pm[e], pa[e], pb[e]), p.slope);
+                else if (p.pro == PRO_ADAIN_SNAKE) {
+                  const float wv = fmaf(x - pm[e], pa[e], pb[e]);
+                  const float sn = __sinf(pal[e] * wv);
+                  x = fmaf(pia[e], sn * sn, wv);
+                }
+                v[h][e] = (c0 + e < p.Cin) ? x : 0.f;
+              }
+            }
+            uint4 o;
+            if (p.wfmt == 1) { o.x = pack_f16(v[h][0], v[h][1]); o.y = pack_f16(v[h][2], v[h][3]); o.z = pack_f16(v[h][4], v[h][5]); o.w = pack_f16(v[h][6], v[h][7]); }
+            else { o.x = pack_bf16(v[h][0], v[h][1]); o.y = pack_bf16(v[h][2], v[h][3]); o.z = pack_bf16(v[h][4], v[h][5]); o.w = pack_bf16(v[h][6], v[h][7]); }
+            *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
+          }
         }
-        if (lane < 8) {          // one writer per (row quadrant, channel): plain stores, fixed-order sum below => deterministic
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { s_sum[q * 256 + c0 + cc + e] = ps[e]; s_sq[q * 256 + c0 + cc + e] = pq[e]; }
-        }
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
+        mbar_arrive(bar_slab_full(b));
       }
-    }
-    tc_fence_before();
-    asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
-    if (p.ostats && tid < pl.BN && n0 + tid < p.Cout) {
-      double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + n0 + tid) * 2;
-      const float ts = (s_sum[tid] + s_sum[256 + tid]) + (s_sum[512 + tid] + s_sum[768 + tid]);
-      const float tq = (s_sq[tid] + s_sq[256 + tid]) + (s_sq[512 + tid] + s_sq[768 + tid]);
-      atomicAdd(st, (double)ts);
-      atomicAdd(st + 1, (double)tq);
     }
   } else if (warp == NPW) {
     // =================== weight loader (bulk-copy engine) ===================
     if (lane == 0) {
-      const uint16_t* wsrc = p.wb + (size_t)nt * p.k * pl.kcn * (size_t)(pl.BN * KCH);
       uint32_t it = 0;
-      for (int sc = 0; sc < pl.nsc; ++sc)
-        for (int j = 0; j < p.k; ++j)
-          for (int kc = 0; kc < nwst; ++kc, ++it) {
-            const uint32_t s = it % NSTAGE;
-            mbar_wait(bar_empty(s), ((it / NSTAGE) & 1u) ^ 1u);
-            mbar_expect_tx(bar_full(s), pl.wstage_bytes);
-            const size_t blk = (size_t)j * pl.kcn + (size_t)sc * nwst + kc;
-            bulk_g2s(w0 + s * pl.wstage_bytes, wsrc + blk * (size_t)(pl.BN * KCH), pl.wstage_bytes, bar_full(s));
-          }
+      for (int item = item0; item < item1; ++item) {
+        const int nt = item / p.ntiles;
+        const uint16_t* wsrc = p.wb + (size_t)nt * p.k * pl.kcn * (size_t)(pl.BN * KCH);
+        for (int sc = 0; sc < pl.nsc; ++sc)
+          for (int j = 0; j < p.k; ++j)
+            for (int kc = 0; kc < nwst; ++kc, ++it) {
+              const uint32_t s = it % NS;
+              mbar_wait(bar_empty(s), ((it / NS) & 1u) ^ 1u);
+              mbar_expect_tx(bar_full(s), pl.wstage_bytes);
+              const size_t blk = (size_t)j * pl.kcn + (size_t)sc * nwst + kc;
+              bulk_g2s(w0 + s * pl.wstage_bytes, wsrc + blk * (size_t)(pl.BN * KCH), pl.wstage_bytes, bar_full(s));
+            }
+      }
     }
-  } else {
+  } else if (warp == NPW + 1) {
     // =================== MMA issuer ===================
     if (lane == 0) {
       const uint32_t ofmt = p.wfmt == 1 ? 0u : 1u;     // instruction-descriptor operand format: 0 = F16, 1 = BF16
       const uint32_t idesc = (1u << 4) | (ofmt << 7) | (ofmt << 10) | ((uint32_t)(pl.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_lbo = (uint32_t)pl.SR * 16u, a_sbo = 128u;
       const uint32_t b_lbo = (uint32_t)pl.BN * 16u, b_sbo = 128u;
-      uint32_t it = 0;
-      for (int sc = 0; sc < pl.nsc; ++sc) {
-        const int b = sc % pl.nslab;
-        mbar_wait(bar_slab_full(b), ((uint32_t)(sc / pl.nslab)) & 1u);
+      uint32_t it = 0, g = 0, n = 0;
+      for (int item = item0; item < item1; ++item, ++n) {
+        const uint32_t slot = n & 1u;
+        mbar_wait(bar_acc_empty(slot), ((n >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sbase = slab0 + (uint32_t)b * pl.slab_bytes;
-        for (int j = 0; j < p.k; ++j)
-          for (int kc = 0; kc < nwst; ++kc, ++it) {
-            const uint32_t s = it % NSTAGE;
-            mbar_wait(bar_full(s), (it / NSTAGE) & 1u);
-            tc_fence_after();
-            const uint32_t wbase = w0 + s * pl.wstage_bytes;
+        const uint32_t tacc = tmem_base + slot * (uint32_t)pl.BN;
+        uint32_t first = 1;
+        for (int sc = 0; sc < pl.nsc; ++sc, ++g) {
+          const uint32_t b = g & 1u;
+          mbar_wait(bar_slab_full(b), (g >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t sbase = slab0 + b * pl.slab_bytes;
+          for (int j = 0; j < p.k; ++j)
+            for (int kc = 0; kc < nwst; ++kc, ++it) {
+              const uint32_t s = it % NS;
+              mbar_wait(bar_full(s), (it / NS) & 1u);
+              tc_fence_after();
+              const uint32_t wbase = w0 + s * pl.wstage_bytes;
 #pragma unroll
-            for (int kk = 0; kk < KCH / 16; ++kk) {
-              const uint32_t aaddr = sbase + (uint32_t)(((kc * 8 + kk * 2) * pl.SR + j * p.dil) * 16);
-              const uint32_t baddr = wbase + (uint32_t)(kk * 2 * pl.BN * 16);
-              const uint64_t ad = make_desc(aaddr, a_lbo, a_sbo);
-              const uint64_t bd = make_desc(baddr, b_lbo, b_sbo);
-              umma_bf16(tmem_base, ad, bd, idesc, (it | (uint32_t)kk) != 0u);
+              for (int kk = 0; kk < KCH / 16; ++kk) {
+                const uint32_t aaddr = sbase + (uint32_t)(((kc * 8 + kk * 2) * pl.SR + j * p.dil) * 16);
+                const uint32_t baddr = wbase + (uint32_t)(kk * 2 * pl.BN * 16);
+                umma_bf16(tacc, make_desc(aaddr, a_lbo, a_sbo), make_desc(baddr, b_lbo, b_sbo), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              umma_commit(bar_empty(s));            // weight stage free once these MMAs have read it
             }
-            umma_commit(bar_empty(s));          // stage free once these MMAs have read it
-          }
-        umma_commit(bar_slab_empty(b));          // slab free once every MMA issued so far has completed
+          umma_commit(bar_slab_empty(b));           // slab free once every MMA issued so far has completed
+        }
+        umma_commit(bar_acc_full(slot));            // accumulator of this item complete
       }
-      umma_commit(bar_acc);                      // accumulator complete
     }
+  } else {
+    // =================== epilogue (4 warps, one TMEM lane quadrant each) ===================
+    const int q = warp & 3;
+    const int et = tid - (NPROD + 64);                 // 0..127
+    float* stg = reinterpret_cast<float*>(smem + pl.off_stg + (size_t)(warp - (NPW + 2)) * STG_BYTES);
+    const int nchunk = pl.BN >> 5;
+    const int cc = (lane & 7) * 4;
+    uint32_t n = 0;
+    for (int item = item0; item < item1; ++item, ++n) {
+      const int nt = item / p.ntiles;
+      const Tile tile = p.tiles[item % p.ntiles];
+      const Seg seg = p.segs[tile.seg];
+      const int n0 = nt * pl.BN;
+      const uint32_t slot = n & 1u;
+      mbar_wait(bar_acc_full(slot), (n >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + slot * (uint32_t)pl.BN + ((uint32_t)(q * 32) << 16);
+      for (int chunk = 0; chunk < nchunk; ++chunk) {
+        const int c0 = chunk * 32;
+        const int co = n0 + c0 + cc;
+        uint32_t v[32];
+        tmem_ld32(tacc + (uint32_t)c0, v);
+        if (chunk == nchunk - 1) {                     // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(bar_acc_empty(slot));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 f;
+          f.x = __uint_as_float(v[4 * i]); f.y = __uint_as_float(v[4 * i + 1]); f.z = __uint_as_float(v[4 * i + 2]); f.w = __uint_as_float(v[4 * i + 3]);
+          *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * i) = f;
+        }
+        __syncwarp();
+        float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool colok = co < p.Cout;
+        const bool full4 = co + 3 < p.Cout;
+        if (colok && full4) {
+          // all global reads of the chunk first (res / y may alias the output, so the compiler cannot hoist them itself)
+          float4 r4[8], y4[8];
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + co);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int t = tile.t0 + q * 32 + 4 * i + (lane >> 3);
+            r4[i] = make_float4(0.f, 0.f, 0.f, 0.f); y4[i] = r4[i];
+            if (t < seg.out_len) {
+              const size_t orow = (size_t)(seg.out_off + t);
+              if (p.res) r4[i] = *reinterpret_cast<const float4*>(p.res + orow * p.ldr + co);
+              if (p.accumulate) y4[i] = *reinterpret_cast<const float4*>(p.y + orow * p.ldy + co);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            const int t = tile.t0 + q * 32 + rr;
+            if (t < seg.out_len) {
+              const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
+              float4 o;
+              o.x = (a4.x + b4.x + r4[i].x) * p.out_scale + y4[i].x;
+              o.y = (a4.y + b4.y + r4[i].y) * p.out_scale + y4[i].y;
+              o.z = (a4.z + b4.z + r4[i].z) * p.out_scale + y4[i].z;
+              o.w = (a4.w + b4.w + r4[i].w) * p.out_scale + y4[i].w;
+              *reinterpret_cast<float4*>(p.y + (size_t)(seg.out_off + t) * p.ldy + co) = o;
+              ps[0] += o.x; ps[1] += o.y; ps[2] += o.z; ps[3] += o.w;
+              pq[0] += o.x * o.x; pq[1] += o.y * o.y; pq[2] += o.z * o.z; pq[3] += o.w * o.w;
+            }
+          }
+        } else if (colok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            const int t = tile.t0 + q * 32 + rr;
+            if (t < seg.out_len) {
+              const size_t orow = (size_t)(seg.out_off + t);
+              float* dst = p.y + orow * p.ldy + co;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (co + e < p.Cout) {
+                  float xv = stg[rr * STG_LD + cc + e];
+                  if (p.bias) xv += p.bias[co + e];
+                  if (p.res) xv += p.res[orow * p.ldr + co + e];
+                  xv *= p.out_scale;
+                  if (p.accumulate) xv += dst[e];
+                  dst[e] = xv;
+                  ps[e] += xv; pq[e] += xv * xv;
+                }
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (p.ostats) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);  pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 8);
+            ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16); pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 16);
+          }
+          if (lane < 8) {        // one owner per (row quadrant, channel): running sums over this CTA's consecutive tiles
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { s_sum[q * 256 + c0 + cc + e] += (double)ps[e]; s_sq[q * 256 + c0 + cc + e] += (double)pq[e]; }
+          }
+        }
+      }
+      if (p.ostats) {
+        // flush the per-CTA statistics when the (utterance, Cout tile) changes or the CTA is done
+        bool flush = item + 1 >= item1;
+        if (!flush) {
+          const int nitem = item + 1;
+          flush = (nitem / p.ntiles != nt) || (p.tiles[nitem % p.ntiles].seg != tile.seg);
+        }
+        if (flush) {
+          asm volatile("bar.sync 2, %0;" ::"n"(NEPI) : "memory");
+          for (int c = et; c < pl.BN; c += NEPI) {
+            if (n0 + c < p.Cout) {
+              const double ts = (s_sum[c] + s_sum[256 + c]) + (s_sum[512 + c] + s_sum[768 + c]);
+              const double tq = (s_sq[c] + s_sq[256 + c]) + (s_sq[512 + c] + s_sq[768 + c]);
+              double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + n0 + c) * 2;
+              atomicAdd(st, ts);
+              atomicAdd(st + 1, tq);
+            }
+            s_sum[c] = 0.0; s_sum[256 + c] = 0.0; s_sum[512 + c] = 0.0; s_sum[768 + c] = 0.0;
+            s_sq[c] = 0.0; s_sq[256 + c] = 0.0; s_sq[512 + c] = 0.0; s_sq[768 + c] = 0.0;
+          }
+          asm volatile("bar.sync 2, %0;" ::"n"(NEPI) : "memory");
+        }
+      }
+    }
+    tc_fence_before();
   }
   __syncthreads();
   if (warp == NPW + 1) tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
@@ -369,6 +462,8 @@ void pads(int Cin, int Cout, int& cin_pad, int& cout_pad, int& BN) {
   else { cout_pad = round_up(Cout, 256); BN = 256; }
 }
 
+int g_num_sms = 0;
+
 bool make_plan(const ConvArgs& a, Plan& pl) {
   int cin_pad, cout_pad, BN;
   pads(a.Cin, a.Cout, cin_pad, cout_pad, BN);
@@ -377,26 +472,28 @@ bool make_plan(const ConvArgs& a, Plan& pl) {
   pl.ntile_n = cout_pad / BN;
   pl.KS = cin_pad < 128 ? cin_pad : 128;
   pl.nsc = cin_pad / pl.KS;
-  pl.nslab = pl.nsc > 1 ? 2 : 1;
   pl.kcn = cin_pad / KCH;
   pl.SR = (BM + (a.k - 1) * a.dil) | 1;
   int tc = 32;
-  while (tc < BN) tc <<= 1;
+  while (tc < 2 * BN) tc <<= 1;                    // two accumulators
   pl.tmem_cols = tc;
   uint32_t off = 16;
-  pl.off_bar = off; off += 128;
-  pl.off_stats = off; off += 2048 * 4;
+  pl.off_bar = off; off += 8u * (2 * MAXSTAGE + 8);
+  off = (off + 15u) & ~15u;
+  pl.off_stats = off; off += 2048 * 8;
   pl.off_par = off; off += 5u * cin_pad * 4u;
+  off = (off + 15u) & ~15u;
+  pl.off_stg = off; off += (NEPI / 32) * STG_BYTES;
   off = (off + 127u) & ~127u;
   pl.off_slab = off;
   pl.slab_bytes = (uint32_t)(pl.KS / 8) * pl.SR * 16u;
   pl.slab_bytes = (pl.slab_bytes + 127u) & ~127u;
-  uint32_t slab_total = pl.slab_bytes * pl.nslab;
   pl.wstage_bytes = (uint32_t)BN * KCH * 2u;
-  uint32_t region = slab_total + NSTAGE * pl.wstage_bytes;
-  if (region < (uint32_t)(NPW * STG_BYTES)) region = NPW * STG_BYTES;      // the epilogue staging tiles alias this region
-  pl.off_w = pl.off_slab + slab_total;
-  pl.smem_bytes = pl.off_slab + region;
+  pl.off_w = pl.off_slab + 2 * pl.slab_bytes;
+  pl.nstage = MAXSTAGE;
+  while (pl.nstage > 2 && pl.off_w + pl.nstage * pl.wstage_bytes > 227u * 1024u) --pl.nstage;
+  pl.smem_bytes = pl.off_w + pl.nstage * pl.wstage_bytes;
+  pl.items = a.ntiles * pl.ntile_n;
   return pl.smem_bytes <= 227u * 1024u;
 }
 
@@ -450,7 +547,16 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid(a.ntiles, u.p.ntile_n);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+  }
+  const int ncta = u.p.items < g_num_sms ? u.p.items : g_num_sms;      // persistent: one CTA per SM
+  u.p.per_cta = (u.p.items + ncta - 1) / ncta;
+  const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
   conv_umma_kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
   return launched();
 }
