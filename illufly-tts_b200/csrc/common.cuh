@@ -36,7 +36,8 @@ struct ConvArgs {
   const float* x; int ldx;
   const float* w; int ldw;             // [k][Cin][ldw], ldw = Cout rounded up to 4
   const uint16_t* wb;                  // tensor-core path: 16-bit operand image of the weights (conv_umma.cu), else null
-  int wfmt;                            // operand format of wb and of the activation slab: 0 = bf16, 1 = fp16
+  int wfmt;                            // operand format of wb and of the activation slab: 0 = bf16, 1 = fp16,
+                                       // 2 = split fp16 (x = hi + lo, 3 MMAs per K step: fp32-equivalent products)
   int cin_pad, cout_pad;
   const float* bias;
   float* y; int ldy;
@@ -47,6 +48,7 @@ struct ConvArgs {
   const float* gb; int ld_gb; int beta_off;  // gamma = gb[seg*ld_gb + c], beta = gb[seg*ld_gb + beta_off + c]
   const float* alpha;                  // [Cin] Snake
   float out_scale; int accumulate; int act; float act_slope;
+  float acc_scale;                     // tensor path: accumulator * acc_scale before bias (undoes the split-mode operand scaling); 0 = 1
   double* ostats; int ld_ostats;       // [nseg][ld_ostats][2]
   const Seg* segs; const Tile* tiles; int ntiles; int tile_rows;
 };

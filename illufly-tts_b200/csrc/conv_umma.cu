@@ -30,12 +30,14 @@ constexpr int NPROD = NPW * 32;
 constexpr int NEPI = 128;               // 4 epilogue warps (one per TMEM lane quadrant)
 constexpr int NTHREADS = NPROD + 64 + NEPI;   // producers (0-7), weight loader (8), MMA issuer (9), epilogue (10-13)
 constexpr int MAXSTAGE = 4;
+// split-fp16 mode: operands are pre-scaled by powers of two so that the low halves stay in fp16's normal range
+constexpr float SPLIT_SA = 16.f, SPLIT_SW = 256.f;
 constexpr int STG_LD = 36;              // floats per staging row (32 + 4 pad: 16-B aligned rows, conflict-free both ways)
 constexpr int STG_BYTES = 32 * STG_LD * 4;
 constexpr uint32_t SPIN_LIMIT = 40u * 1000u * 1000u;
 
 struct Plan {
-  int BN, KS, nsc, SR, kcn, tmem_cols, ntile_n, nstage, items, per_cta;
+  int BN, KS, nsc, SR, kcn, tmem_cols, ntile_n, nstage, items, per_cta, split, acc_cols;
   uint32_t off_bar, off_stats, off_par, off_stg, off_slab, slab_bytes, off_w, wstage_bytes, smem_bytes;
 };
 
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           }
         }
         uint8_t* slab = smem + pl.off_slab + (size_t)b * pl.slab_bytes + (size_t)pln * pl.SR * 16;
+        const size_t lo_off = (size_t)planes * pl.SR * 16;      // split mode: the low halves follow the high planes
         const bool second = c0 + 4 < p.ldx;
         // two rows per iteration: four 16-B loads in flight per thread before any arithmetic
         for (int r = r0; r < pl.SR; r += 2 * rpp) {
@@ -255,7 +258,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
               }
             }
             uint4 o;
-            if (p.wfmt == 1) { o.x = pack_f16(v[h][0], v[h][1]); o.y = pack_f16(v[h][2], v[h][3]); o.z = pack_f16(v[h][4], v[h][5]); o.w = pack_f16(v[h][6], v[h][7]); }
+            if (p.wfmt == 2) {
+              uint4 ol;
+              float hi[8], lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float xs = fminf(fmaxf(v[h][e] * SPLIT_SA, -65504.f), 65504.f);
+                hi[e] = __half2float(__float2half_rn(xs));
+                lo[e] = xs - hi[e];                        // exact in fp32; its own fp16 rounding error is ~2^-22 of x
+              }
+              o.x = pack_f16(hi[0], hi[1]); o.y = pack_f16(hi[2], hi[3]); o.z = pack_f16(hi[4], hi[5]); o.w = pack_f16(hi[6], hi[7]);
+              ol.x = pack_f16(lo[0], lo[1]); ol.y = pack_f16(lo[2], lo[3]); ol.z = pack_f16(lo[4], lo[5]); ol.w = pack_f16(lo[6], lo[7]);
+              *reinterpret_cast<uint4*>(slab + lo_off + (size_t)rr * 16) = ol;
+            }
+            else if (p.wfmt == 1) { o.x = pack_f16(v[h][0], v[h][1]); o.y = pack_f16(v[h][2], v[h][3]); o.z = pack_f16(v[h][4], v[h][5]); o.w = pack_f16(v[h][6], v[h][7]); }
             else { o.x = pack_bf16(v[h][0], v[h][1]); o.y = pack_bf16(v[h][2], v[h][3]); o.z = pack_bf16(v[h][4], v[h][5]); o.w = pack_bf16(v[h][6], v[h][7]); }
             *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
           }
@@ -270,7 +286,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       uint32_t it = 0;
       for (int item = item0; item < item1; ++item) {
         const int nt = item / p.ntiles;
-        const uint16_t* wsrc = p.wb + (size_t)nt * p.k * pl.kcn * (size_t)(pl.BN * KCH);
+        const size_t stage_elems = (size_t)pl.wstage_bytes / 2;
+        const uint16_t* wsrc = p.wb + (size_t)nt * p.k * pl.kcn * stage_elems;
         for (int sc = 0; sc < pl.nsc; ++sc)
           for (int j = 0; j < p.k; ++j)
             for (int kc = 0; kc < nwst; ++kc, ++it) {
@@ -278,14 +295,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
               mbar_wait(bar_empty(s), ((it / NS) & 1u) ^ 1u);
               mbar_expect_tx(bar_full(s), pl.wstage_bytes);
               const size_t blk = (size_t)j * pl.kcn + (size_t)sc * nwst + kc;
-              bulk_g2s(w0 + s * pl.wstage_bytes, wsrc + blk * (size_t)(pl.BN * KCH), pl.wstage_bytes, bar_full(s));
+              bulk_g2s(w0 + s * pl.wstage_bytes, wsrc + blk * stage_elems, pl.wstage_bytes, bar_full(s));
             }
       }
     }
   } else if (warp == NPW + 1) {
     // =================== MMA issuer ===================
     if (lane == 0) {
-      const uint32_t ofmt = p.wfmt == 1 ? 0u : 1u;     // instruction-descriptor operand format: 0 = F16, 1 = BF16
+      const uint32_t ofmt = p.wfmt >= 1 ? 0u : 1u;     // instruction-descriptor operand format: 0 = F16, 1 = BF16
+      const uint32_t a_lo = (uint32_t)(pl.KS >> 3) * (uint32_t)pl.SR * 16u;     // split mode: offset of the low-half planes
+      const uint32_t b_lo = (uint32_t)pl.BN * KCH * 2u;                         //             and of the low-half weight block
       const uint32_t idesc = (1u << 4) | (ofmt << 7) | (ofmt << 10) | ((uint32_t)(pl.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_lbo = (uint32_t)pl.SR * 16u, a_sbo = 128u;
       const uint32_t b_lbo = (uint32_t)pl.BN * 16u, b_sbo = 128u;
@@ -294,7 +313,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         const uint32_t slot = n & 1u;
         mbar_wait(bar_acc_empty(slot), ((n >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tacc = tmem_base + slot * (uint32_t)pl.BN;
+        const uint32_t tacc = tmem_base + slot * (uint32_t)pl.acc_cols;
+        const uint32_t tcor = tacc + (uint32_t)pl.BN;       // split mode: the small cross terms get their own accumulator
         uint32_t first = 1;
         for (int sc = 0; sc < pl.nsc; ++sc, ++g) {
           const uint32_t b = g & 1u;
@@ -312,6 +332,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
                 const uint32_t aaddr = sbase + (uint32_t)(((kc * 8 + kk * 2) * pl.SR + j * p.dil) * 16);
                 const uint32_t baddr = wbase + (uint32_t)(kk * 2 * pl.BN * 16);
                 umma_bf16(tacc, make_desc(aaddr, a_lbo, a_sbo), make_desc(baddr, b_lbo, b_sbo), idesc, first ? 0u : 1u);
+                if (pl.split) {
+                  // x w ~= xh wh + (xh wl + xl wh)   (xl wl is ~2^-22 relative and dropped).  The tensor core truncates at
+                  // every accumulate, an error that grows linearly with the number of MMAs into one accumulator: the cross
+                  // terms (2^-11 of the main term) go to their own accumulator, so the main one sees K/16 steps, not 3K/16
+                  umma_bf16(tcor, make_desc(aaddr, a_lbo, a_sbo), make_desc(baddr + b_lo, b_lbo, b_sbo), idesc, first ? 0u : 1u);
+                  umma_bf16(tcor, make_desc(aaddr + a_lo, a_lbo, a_sbo), make_desc(baddr, b_lbo, b_sbo), idesc, 1u);
+                }
                 first = 0;
               }
               umma_commit(bar_empty(s));            // weight stage free once these MMAs have read it
@@ -328,6 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     float* stg = reinterpret_cast<float*>(smem + pl.off_stg + (size_t)(warp - (NPW + 2)) * STG_BYTES);
     const int nchunk = pl.BN >> 5;
     const int cc = (lane & 7) * 4;
+    const float acs = p.acc_scale != 0.f ? p.acc_scale : 1.0f;
     uint32_t n = 0;
     for (int item = item0; item < item1; ++item, ++n) {
       const int nt = item / p.ntiles;
@@ -337,12 +365,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       const uint32_t slot = n & 1u;
       mbar_wait(bar_acc_full(slot), (n >> 1) & 1u);
       tc_fence_after();
-      const uint32_t tacc = tmem_base + slot * (uint32_t)pl.BN + ((uint32_t)(q * 32) << 16);
+      const uint32_t tacc = tmem_base + slot * (uint32_t)pl.acc_cols + ((uint32_t)(q * 32) << 16);
       for (int chunk = 0; chunk < nchunk; ++chunk) {
         const int c0 = chunk * 32;
         const int co = n0 + c0 + cc;
         uint32_t v[32];
         tmem_ld32(tacc + (uint32_t)c0, v);
+        if (pl.split) {
+          uint32_t v2[32];
+          tmem_ld32(tacc + (uint32_t)(pl.BN + c0), v2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+        }
         if (chunk == nchunk - 1) {                     // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(bar_acc_empty(slot));
@@ -379,10 +413,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             if (t < seg.out_len) {
               const float4 a4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + cc);
               float4 o;
-              o.x = (a4.x + b4.x + r4[i].x) * p.out_scale + y4[i].x;
-              o.y = (a4.y + b4.y + r4[i].y) * p.out_scale + y4[i].y;
-              o.z = (a4.z + b4.z + r4[i].z) * p.out_scale + y4[i].z;
-              o.w = (a4.w + b4.w + r4[i].w) * p.out_scale + y4[i].w;
+              o.x = fmaf(a4.x, acs, b4.x) + r4[i].x; o.y = fmaf(a4.y, acs, b4.y) + r4[i].y;
+              o.z = fmaf(a4.z, acs, b4.z) + r4[i].z; o.w = fmaf(a4.w, acs, b4.w) + r4[i].w;
+              if (p.act == ACT_GELU_NEW) { o.x = gelu_new(o.x); o.y = gelu_new(o.y); o.z = gelu_new(o.z); o.w = gelu_new(o.w); }
+              o.x = o.x * p.out_scale + y4[i].x; o.y = o.y * p.out_scale + y4[i].y;
+              o.z = o.z * p.out_scale + y4[i].z; o.w = o.w * p.out_scale + y4[i].w;
               *reinterpret_cast<float4*>(p.y + (size_t)(seg.out_off + t) * p.ldy + co) = o;
               ps[0] += o.x; ps[1] += o.y; ps[2] += o.z; ps[3] += o.w;
               pq[0] += o.x * o.x; pq[1] += o.y * o.y; pq[2] += o.z * o.z; pq[3] += o.w * o.w;
@@ -399,9 +434,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 if (co + e < p.Cout) {
-                  float xv = stg[rr * STG_LD + cc + e];
+                  float xv = stg[rr * STG_LD + cc + e] * acs;
                   if (p.bias) xv += p.bias[co + e];
                   if (p.res) xv += p.res[orow * p.ldr + co + e];
+                  if (p.act == ACT_GELU_NEW) xv = gelu_new(xv);
                   xv *= p.out_scale;
                   if (p.accumulate) xv += dst[e];
                   dst[e] = xv;
@@ -456,39 +492,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-void pads(int Cin, int Cout, int& cin_pad, int& cout_pad, int& BN) {
-  cin_pad = Cin <= 64 ? 64 : round_up(Cin, 128);
-  if (Cout <= 256) { cout_pad = round_up(Cout, 32); BN = cout_pad; }
-  else { cout_pad = round_up(Cout, 256); BN = 256; }
+void pads(int Cin, int Cout, bool split, int& cin_pad, int& cout_pad, int& BN) {
+  const int bnmax = split ? 128 : 256;       // split mode streams two weight blocks per stage: halve the Cout tile
+  cin_pad = split ? round_up(Cin, 64) : (Cin <= 64 ? 64 : round_up(Cin, 128));
+  if (Cout <= bnmax) { cout_pad = round_up(Cout, 32); BN = cout_pad; }
+  else { cout_pad = round_up(Cout, bnmax); BN = bnmax; }
 }
 
 int g_num_sms = 0;
 
 bool make_plan(const ConvArgs& a, Plan& pl) {
   int cin_pad, cout_pad, BN;
-  pads(a.Cin, a.Cout, cin_pad, cout_pad, BN);
+  pl.split = a.wfmt == 2 ? 1 : 0;
+  pads(a.Cin, a.Cout, pl.split != 0, cin_pad, cout_pad, BN);
   if (cin_pad != a.cin_pad || cout_pad != a.cout_pad) return false;
   pl.BN = BN;
   pl.ntile_n = cout_pad / BN;
-  pl.KS = cin_pad < 128 ? cin_pad : 128;
+  pl.KS = pl.split ? 64 : (cin_pad < 128 ? cin_pad : 128);
   pl.nsc = cin_pad / pl.KS;
   pl.kcn = cin_pad / KCH;
   pl.SR = (BM + (a.k - 1) * a.dil) | 1;
+  pl.acc_cols = pl.split ? 2 * BN : BN;
   int tc = 32;
-  while (tc < 2 * BN) tc <<= 1;                    // two accumulators
+  while (tc < 2 * pl.acc_cols) tc <<= 1;           // two accumulator buffers
   pl.tmem_cols = tc;
   uint32_t off = 16;
   pl.off_bar = off; off += 8u * (2 * MAXSTAGE + 8);
   off = (off + 15u) & ~15u;
   pl.off_stats = off; off += 2048 * 8;
-  pl.off_par = off; off += 5u * cin_pad * 4u;
+  pl.off_par = off; off += a.pro >= PRO_ADAIN_LRELU ? 5u * cin_pad * 4u : 0u;
   off = (off + 15u) & ~15u;
   pl.off_stg = off; off += (NEPI / 32) * STG_BYTES;
   off = (off + 127u) & ~127u;
   pl.off_slab = off;
-  pl.slab_bytes = (uint32_t)(pl.KS / 8) * pl.SR * 16u;
+  pl.slab_bytes = (uint32_t)(pl.KS / 8) * pl.SR * 16u * (pl.split ? 2u : 1u);
   pl.slab_bytes = (pl.slab_bytes + 127u) & ~127u;
-  pl.wstage_bytes = (uint32_t)BN * KCH * 2u;
+  pl.wstage_bytes = (uint32_t)BN * KCH * 2u * (pl.split ? 2u : 1u);
   pl.off_w = pl.off_slab + 2 * pl.slab_bytes;
   pl.nstage = MAXSTAGE;
   while (pl.nstage > 2 && pl.off_w + pl.nstage * pl.wstage_bytes > 227u * 1024u) --pl.nstage;
@@ -502,9 +541,11 @@ bool make_plan(const ConvArgs& a, Plan& pl) {
 // 16-bit (bf16 or fp16) image of the weights: [Cout tile][tap][64-channel chunk][8-channel plane][BN rows][8 channels]
 void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fmt, std::vector<uint16_t>& out, int& cin_pad, int& cout_pad) {
   int BN;
-  pads(Cin, Cout, cin_pad, cout_pad, BN);
+  const bool split = fmt == 2;
+  pads(Cin, Cout, split, cin_pad, cout_pad, BN);
   const int kcn = cin_pad / KCH, ntn = cout_pad / BN;
-  out.assign((size_t)ntn * k * kcn * BN * KCH, (uint16_t)0);
+  const size_t blk = (size_t)BN * KCH * (split ? 2 : 1);          // one stage: [hi block][lo block] in split mode
+  out.assign((size_t)ntn * k * kcn * blk, (uint16_t)0);
   for (int nt = 0; nt < ntn; ++nt)
     for (int j = 0; j < k; ++j)
       for (int kc = 0; kc < kcn; ++kc)
@@ -512,12 +553,18 @@ void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fm
           for (int n = 0; n < BN; ++n) {
             const int co = nt * BN + n;
             if (co >= Cout) continue;
-            const size_t base = (((((size_t)nt * k + j) * kcn + kc) * 8 + pln) * BN + n) * 8;
+            const size_t base = (((size_t)nt * k + j) * kcn + kc) * blk + ((size_t)pln * BN + n) * 8;
             for (int e = 0; e < 8; ++e) {
               const int ci = kc * KCH + pln * 8 + e;
               if (ci < Cin) {
                 const float v = w[((size_t)j * Cin + ci) * ldw + co];
-                if (fmt == 1) { const __half hv = __float2half(v); out[base + e] = *reinterpret_cast<const uint16_t*>(&hv); }
+                if (split) {
+                  const float vs = v * SPLIT_SW;
+                  const __half hv = __float2half(vs);
+                  const __half lv = __float2half(vs - __half2float(hv));
+                  out[base + e] = *reinterpret_cast<const uint16_t*>(&hv);
+                  out[base + (size_t)BN * KCH + e] = *reinterpret_cast<const uint16_t*>(&lv);
+                } else if (fmt == 1) { const __half hv = __float2half(v); out[base + e] = *reinterpret_cast<const uint16_t*>(&hv); }
                 else { const __nv_bfloat16 bv = __float2bfloat16(v); out[base + e] = *reinterpret_cast<const uint16_t*>(&bv); }
               }
             }
@@ -525,7 +572,7 @@ void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fm
 }
 
 bool conv_umma_supported(const ConvArgs& a) {
-  if (!a.wb || a.stride != 1 || a.act != ACT_NONE) return false;
+  if (!a.wb || a.stride != 1 || (a.act != ACT_NONE && a.act != ACT_GELU_NEW)) return false;
   if (a.in_shr != 0 && (a.k != 1 || a.pad != 0)) return false;
   if ((a.ldx & 3) || (reinterpret_cast<uintptr_t>(a.x) & 15)) return false;
   if ((a.ldy & 3) || (reinterpret_cast<uintptr_t>(a.y) & 15)) return false;
@@ -541,6 +588,7 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   UArgs u;
   u.a = a;
   if (!make_plan(a, u.p)) return cudaErrorInvalidValue;
+  if (a.wfmt == 2) u.a.acc_scale = 1.0f / (SPLIT_SA * SPLIT_SW);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -128,18 +128,19 @@ struct Loader {
     return true;
   }
   // torch Conv1d weight [Cout, Cin, k] (or Linear [Cout, Cin]) -> ConvW
-  void pack_conv(const HostTensor& w, const std::vector<float>* bias, ConvW& c, bool want_bf16);
-  bool conv(const std::string& prefix, ConvW& c, bool has_bias = true, bool want_bf16 = false) {
+  // want: bit 0 = 16-bit tensor-core packs (bf16 + fp16), bit 1 = split-fp16 pack (fp32-equivalent)
+  void pack_conv(const HostTensor& w, const std::vector<float>* bias, ConvW& c, int want);
+  bool conv(const std::string& prefix, ConvW& c, bool has_bias = true, int want = 0) {
     HostTensor w;
     if (!weight(prefix, w)) return false;
     const HostTensor* b = has_bias ? get(prefix + ".bias") : nullptr;
     if (has_bias && !b) return false;
-    pack_conv(w, b ? &b->data : nullptr, c, want_bf16);
+    pack_conv(w, b ? &b->data : nullptr, c, want);
     return true;
   }
   bool lstm(const std::string& prefix, LstmW& l);
   bool resblk1d(const std::string& prefix, ResBlk1dW& r, int cin, int cout, bool up, std::vector<float>& style_w, std::vector<float>& style_b,
-                bool want_bf16);
+                int want);
   bool resblock1(const std::string& prefix, ResBlock1W& r, int C, int k, std::vector<float>& style_w, std::vector<float>& style_b);
   // append one AdaIN / AdaLayerNorm fc (Linear 128 -> n) to a concatenated style projection; returns its column offset
   bool style_fc(const std::string& prefix, int n, std::vector<float>& style_w, std::vector<float>& style_b, AdainRef& ref, int C) {
@@ -156,7 +157,7 @@ struct Loader {
   }
 };
 
-void Loader::pack_conv(const HostTensor& w, const std::vector<float>* bias, ConvW& c, bool want_bf16) {
+void Loader::pack_conv(const HostTensor& w, const std::vector<float>* bias, ConvW& c, int want) {
   const int Cout = (int)w.shape[0], Cin = (int)w.shape[1], k = w.shape.size() > 2 ? (int)w.shape[2] : 1;
   c.Cin = Cin; c.Cout = Cout; c.k = k;
   c.ldw = (Cout + 3) & ~3;
@@ -166,12 +167,16 @@ void Loader::pack_conv(const HostTensor& w, const std::vector<float>* bias, Conv
       for (int j = 0; j < k; ++j) p[((size_t)j * Cin + ci) * c.ldw + co] = w.data[((size_t)co * Cin + ci) * k + j];
   c.w = upload(p);
   c.bias = bias ? upload(*bias) : nullptr;
-  if (want_bf16) {
-    std::vector<uint16_t> pb;
+  std::vector<uint16_t> pb;
+  if (want & 1) {
     pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, 0, pb, c.cin_pad, c.cout_pad);
     c.wb = upload(pb);
     pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, 1, pb, c.cin_pad, c.cout_pad);
     c.wh = upload(pb);
+  }
+  if (want & 2) {
+    pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, 2, pb, c.cin_pad_s, c.cout_pad_s);
+    c.ws = upload(pb);
   }
 }
 
@@ -192,7 +197,7 @@ bool Loader::lstm(const std::string& prefix, LstmW& l) {
     memcpy(&w.data[(size_t)d * 1024 * In], wih[d]->data.data(), sizeof(float) * 1024 * In);
     for (int g = 0; g < 1024; ++g) bias[d * 1024 + g] = bih[d]->data[g] + bhh[d]->data[g];
   }
-  pack_conv(w, &bias, l.ih, false);
+  pack_conv(w, &bias, l.ih, 3);
   std::vector<float> t((size_t)2 * 256 * 1024);
   for (int d = 0; d < 2; ++d)
     for (int g = 0; g < 1024; ++g)
@@ -205,10 +210,10 @@ bool Loader::lstm(const std::string& prefix, LstmW& l) {
 }
 
 bool Loader::resblk1d(const std::string& prefix, ResBlk1dW& r, int cin, int cout, bool up, std::vector<float>& sw, std::vector<float>& sb,
-                      bool want_bf16) {
+                      int want) {
   r.cin = cin; r.cout = cout; r.up = up; r.learned_sc = cin != cout;
-  bool ok = conv(prefix + ".conv1", r.conv1, true, want_bf16) && conv(prefix + ".conv2", r.conv2, true, want_bf16);
-  if (r.learned_sc) ok = ok && conv(prefix + ".conv1x1", r.sc, false, want_bf16);
+  bool ok = conv(prefix + ".conv1", r.conv1, true, want) && conv(prefix + ".conv2", r.conv2, true, want);
+  if (r.learned_sc) ok = ok && conv(prefix + ".conv1x1", r.sc, false, want);
   ok = ok && style_fc(prefix + ".norm1.fc", 2 * cin, sw, sb, r.n1, cin) && style_fc(prefix + ".norm2.fc", 2 * cout, sw, sb, r.n2, cout);
   if (up) {
     HostTensor w;
@@ -226,7 +231,7 @@ bool Loader::resblock1(const std::string& prefix, ResBlock1W& r, int C, int k, s
   bool ok = true;
   for (int m = 0; m < 3 && ok; ++m) {
     const std::string i = std::to_string(m);
-    ok = ok && conv(prefix + ".convs1." + i, r.c1[m], true, true) && conv(prefix + ".convs2." + i, r.c2[m], true, true);
+    ok = ok && conv(prefix + ".convs1." + i, r.c1[m], true, 1) && conv(prefix + ".convs2." + i, r.c2[m], true, 1);
     ok = ok && style_fc(prefix + ".adain1." + i + ".fc", 2 * C, sw, sb, r.a1[m], C) && style_fc(prefix + ".adain2." + i + ".fc", 2 * C, sw, sb, r.a2[m], C);
     r.alpha1[m] = upload_named(prefix + ".alpha1." + i);
     r.alpha2[m] = upload_named(prefix + ".alpha2." + i);
@@ -256,7 +261,7 @@ bool pack_convT(Loader& ld, const std::string& prefix, int stride, ConvW& c) {
         dst[1] = w.data[((size_t)ci * Cout + co) * K + r];            // tap 1 reads x[m]
       }
     }
-  ld.pack_conv(p, &bias, c, true);
+  ld.pack_conv(p, &bias, c, 1);
   return true;
 }
 
@@ -276,7 +281,7 @@ int engine_finalize(Engine& e) {
   }
   e.emb_ln_g = ld.upload_named("bert.embeddings.LayerNorm.weight");
   e.emb_ln_b = ld.upload_named("bert.embeddings.LayerNorm.bias");
-  ok = ok && ld.conv("bert.encoder.embedding_hidden_mapping_in", e.map_in);
+  ok = ok && ld.conv("bert.encoder.embedding_hidden_mapping_in", e.map_in, true, 2);
   {  // q | k | v fused into one 768 -> 2304 projection
     const HostTensor *wq = ld.get(L + "attention.query.weight"), *wk = ld.get(L + "attention.key.weight"), *wv = ld.get(L + "attention.value.weight");
     const HostTensor *bq = ld.get(L + "attention.query.bias"), *bk = ld.get(L + "attention.key.bias"), *bv = ld.get(L + "attention.value.bias");
@@ -284,36 +289,36 @@ int engine_finalize(Engine& e) {
       HostTensor w; w.shape = {2304, 768};
       w.data = wq->data; w.data.insert(w.data.end(), wk->data.begin(), wk->data.end()); w.data.insert(w.data.end(), wv->data.begin(), wv->data.end());
       std::vector<float> b = bq->data; b.insert(b.end(), bk->data.begin(), bk->data.end()); b.insert(b.end(), bv->data.begin(), bv->data.end());
-      ld.pack_conv(w, &b, e.qkv, false);
+      ld.pack_conv(w, &b, e.qkv, 2);
     } else ok = false;
   }
-  ok = ok && ld.conv(L + "attention.dense", e.att_dense) && ld.conv(L + "ffn", e.ffn) && ld.conv(L + "ffn_output", e.ffn_out);
+  ok = ok && ld.conv(L + "attention.dense", e.att_dense, true, 2) && ld.conv(L + "ffn", e.ffn, true, 2) && ld.conv(L + "ffn_output", e.ffn_out, true, 2);
   e.att_ln_g = ld.upload_named(L + "attention.LayerNorm.weight"); e.att_ln_b = ld.upload_named(L + "attention.LayerNorm.bias");
   e.full_ln_g = ld.upload_named(L + "full_layer_layer_norm.weight"); e.full_ln_b = ld.upload_named(L + "full_layer_layer_norm.bias");
-  ok = ok && ld.conv("bert_encoder", e.bert_enc);
+  ok = ok && ld.conv("bert_encoder", e.bert_enc, true, 2);
   for (int l = 0; l < 3 && ok; ++l) {
     ok = ok && ld.lstm("predictor.text_encoder.lstms." + std::to_string(2 * l), e.de_lstm[l]);
     ok = ok && ld.style_fc("predictor.text_encoder.lstms." + std::to_string(2 * l + 1) + ".fc", 1024, swP, sbP, e.de_aln[l], 512);
   }
   ok = ok && ld.lstm("predictor.lstm", e.dur_lstm) && ld.lstm("predictor.shared", e.shared_lstm) && ld.lstm("text_encoder.lstm", e.te_lstm);
-  ok = ok && ld.conv("predictor.duration_proj.linear_layer", e.dur_proj);
+  ok = ok && ld.conv("predictor.duration_proj.linear_layer", e.dur_proj, true, 2);
   const int pc[3][2] = {{512, 512}, {512, 256}, {256, 256}};
   for (int i = 0; i < 3 && ok; ++i) {
-    ok = ok && ld.resblk1d("predictor.F0." + std::to_string(i), e.f0_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, true);
-    ok = ok && ld.resblk1d("predictor.N." + std::to_string(i), e.n_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, true);
+    ok = ok && ld.resblk1d("predictor.F0." + std::to_string(i), e.f0_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, 1);
+    ok = ok && ld.resblk1d("predictor.N." + std::to_string(i), e.n_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, 1);
   }
   ok = ok && ld.conv("predictor.F0_proj", e.f0_proj) && ld.conv("predictor.N_proj", e.n_proj);
   e.te_emb = ld.upload_named("text_encoder.embedding.weight");
   for (int l = 0; l < 3 && ok; ++l) {
     const std::string p = "text_encoder.cnn." + std::to_string(l);
-    ok = ok && ld.conv(p + ".0", e.te_cnn[l]);
+    ok = ok && ld.conv(p + ".0", e.te_cnn[l], true, 2);
     e.te_ln_g[l] = ld.upload_named(p + ".1.gamma");
     e.te_ln_b[l] = ld.upload_named(p + ".1.beta");
   }
-  ok = ok && ld.resblk1d("decoder.encode", e.enc_blk, 514, 1024, false, swD, sbD, true);
+  ok = ok && ld.resblk1d("decoder.encode", e.enc_blk, 514, 1024, false, swD, sbD, 1);
   for (int i = 0; i < 4 && ok; ++i)
-    ok = ok && ld.resblk1d("decoder.decode." + std::to_string(i), e.dec_blk[i], 1090, i == 3 ? 512 : 1024, i == 3, swD, sbD, true);
-  ok = ok && ld.conv("decoder.asr_res.0", e.asr_res);
+    ok = ok && ld.resblk1d("decoder.decode." + std::to_string(i), e.dec_blk[i], 1090, i == 3 ? 512 : 1024, i == 3, swD, sbD, 1);
+  ok = ok && ld.conv("decoder.asr_res.0", e.asr_res, true, 1);
   {
     HostTensor w;
     if (ld.weight("decoder.F0_conv", w)) e.f0conv_w = ld.upload(w.data); else ok = false;
@@ -324,16 +329,16 @@ int engine_finalize(Engine& e) {
   const std::string G = "decoder.generator.";
   e.src_lin_w = ld.upload_named(G + "m_source.l_linear.weight");
   e.src_lin_b = ld.upload_named(G + "m_source.l_linear.bias");
-  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, true) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, true);
+  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, 1) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, 1);
   ok = ok && pack_convT(ld, G + "ups.0", 10, e.ups[0]) && pack_convT(ld, G + "ups.1", 6, e.ups[1]);
   ok = ok && ld.resblock1(G + "noise_res.0", e.noise_res[0], 256, 7, swD, sbD) && ld.resblock1(G + "noise_res.1", e.noise_res[1], 128, 11, swD, sbD);
   const int rk[3] = {3, 7, 11};
   for (int i = 0; i < 6 && ok; ++i) ok = ok && ld.resblock1(G + "resblocks." + std::to_string(i), e.resblk[i], i < 3 ? 256 : 128, rk[i % 3], swD, sbD);
-  ok = ok && ld.conv(G + "conv_post", e.conv_post, true, true);
+  ok = ok && ld.conv(G + "conv_post", e.conv_post, true, 1);
   if (ok) {
     HostTensor w;
-    w.shape = {(int64_t)sbP.size(), 128}; w.data = swP; ld.pack_conv(w, &sbP, e.style_pred, false);
-    w.shape = {(int64_t)sbD.size(), 128}; w.data = swD; ld.pack_conv(w, &sbD, e.style_dec, false);
+    w.shape = {(int64_t)sbP.size(), 128}; w.data = swP; ld.pack_conv(w, &sbP, e.style_pred, 0);
+    w.shape = {(int64_t)sbD.size(), 128}; w.data = swD; ld.pack_conv(w, &sbD, e.style_dec, 0);
   }
   if (!ok || !ld.missing.empty()) {
     set_error("finalize: missing or malformed checkpoint tensor '%s'", ld.missing.empty() ? "?" : ld.missing.c_str());
@@ -448,15 +453,17 @@ struct ConvCall {
   const double* pstats = nullptr; const float* gb = nullptr; int ld_gb = 0; AdainRef ad; const float* alpha = nullptr;
   float out_scale = 1.f; int accumulate = 0; int act = ACT_NONE; float act_slope = 0.f;
   double* ostats = nullptr;
-  bool tensor = false;           // eligible for the tcgen05 path when the engine runs in bf16 precision
+  bool tensor = false;           // eligible for the tcgen05 path (16-bit operands) when the engine runs in a tensor precision
+  bool exact = false;            // text side: tcgen05 with split-fp16 operands (fp32-equivalent) in tensor precisions, FFMA in FP32
 };
 
 int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   const bool f16 = r.e.precision == TTSB_PRECISION_FP16;
-  a.x = c.x; a.ldx = c.ldx; a.w = c.w->w; a.ldw = c.w->ldw; a.wb = f16 ? c.w->wh : c.w->wb; a.wfmt = f16 ? 1 : 0;
-  a.cin_pad = c.w->cin_pad; a.cout_pad = c.w->cout_pad;
+  a.x = c.x; a.ldx = c.ldx; a.w = c.w->w; a.ldw = c.w->ldw;
+  if (c.exact) { a.wb = c.w->ws; a.wfmt = 2; a.cin_pad = c.w->cin_pad_s; a.cout_pad = c.w->cout_pad_s; }
+  else { a.wb = f16 ? c.w->wh : c.w->wb; a.wfmt = f16 ? 1 : 0; a.cin_pad = c.w->cin_pad; a.cout_pad = c.w->cout_pad; }
   a.bias = c.w->bias; a.y = c.y; a.ldy = c.ldy; a.res = c.res; a.ldr = c.ldr;
   a.Cin = c.w->Cin; a.Cout = c.w->Cout; a.k = c.w->k; a.dil = c.dil; a.pad = c.pad; a.stride = c.stride; a.in_shr = c.in_shr;
   a.pro = c.pro; a.slope = c.slope;
@@ -470,7 +477,7 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   const double rows = (double)t.out_rows;
   const double fl = 2.0 * rows * a.Cin * a.Cout * a.k;
   const double by = 4.0 * rows * ((double)a.Cout * (1 + (a.res ? 1 : 0) + (a.accumulate ? 1 : 0))) + 4.0 * (double)t.in_rows * a.Cin;
-  if (c.tensor && r.e.precision != TTSB_PRECISION_FP32 && conv_umma_supported(a)) {
+  if ((c.tensor || c.exact) && r.e.precision != TTSB_PRECISION_FP32 && conv_umma_supported(a)) {
     r.e.prof.begin(r.s, PROF_CONV_TENSOR, fl, by);
     CK(launch_conv_umma(a, r.s));
   } else {
@@ -497,8 +504,9 @@ std::vector<LstmGroup> make_lstm_groups(const std::vector<LstmSeg>& segs) {
 }
 
 // x W_ih -> gates, then the recurrence
-int run_bilstm(Run& r, const LstmW& l, const float* x, int ldx, float* gx, float* y, int ldy, const SegTab& t, const LstmGroup* groups, int ngroups) {
-  ConvCall c; c.w = &l.ih; c.x = x; c.ldx = ldx; c.y = gx; c.ldy = 2048;
+int run_bilstm(Run& r, const LstmW& l, const float* x, int ldx, float* gx, float* y, int ldy, const SegTab& t, const LstmGroup* groups, int ngroups,
+               bool exact) {
+  ConvCall c; c.w = &l.ih; c.x = x; c.ldx = ldx; c.y = gx; c.ldy = 2048; c.exact = exact; c.tensor = !exact;
   RC(run_conv(r, c, t));
   r.e.prof.begin(r.s, PROF_LSTM, 2.0 * t.out_rows * 2 * 1024 * 256, 0.0);
   CK(launch_lstm_cluster(gx, l.whh, l.ih.bias, y, ldy, groups, ngroups, r.s));
@@ -704,6 +712,8 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   // ---- tables + inputs, one upload ----
   RC(r.tables_begin((size_t)B * (sizeof(Seg) + 2 * sizeof(LstmGroup) + 260 * sizeof(float)) + (size_t)(R / 128 + B + 8) * sizeof(Tile) + (size_t)R * 16 + 8192));
   e.tabT = r.make_tab(e.spT, e.spT);
+  Space spFlat; spFlat.build({R});                      // Linear layers do not care about utterance boundaries: full 128-row tiles
+  const SegTab tTf = r.make_tab(spFlat, spFlat);
   std::vector<int> h_ids(ids + token_offsets[0], ids + token_offsets[0] + R), h_pos(R), h_r2s(R);
   std::vector<LstmSeg> ls(B), lsq(B);
   std::vector<float> h_speed(B), h_ref(ref_s, ref_s + (size_t)B * 256);
@@ -744,14 +754,14 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   float* FF = r.alloc<float>((size_t)R * 2048);
   if (!E || !H || !QKV || !CTX || !A1 || !TMP || !FF) return TTSB_E_NOMEM;
   CK(launch_albert_embed(d_ids, d_pos, e.emb_word, e.emb_pos, e.emb_type, e.emb_ln_g, e.emb_ln_b, E, R, r.s));
-  { ConvCall c; c.w = &e.map_in; c.x = E; c.ldx = 128; c.y = H; c.ldy = 768; RC(run_conv(r, c, tT)); }
+  { ConvCall c; c.w = &e.map_in; c.x = E; c.ldx = 128; c.y = H; c.ldy = 768; c.exact = true; RC(run_conv(r, c, tTf)); }
   for (int layer = 0; layer < 12; ++layer) {
-    { ConvCall c; c.w = &e.qkv; c.x = H; c.ldx = 768; c.y = QKV; c.ldy = 2304; RC(run_conv(r, c, tT)); }
+    { ConvCall c; c.w = &e.qkv; c.x = H; c.ldx = 768; c.y = QKV; c.ldy = 2304; c.exact = true; RC(run_conv(r, c, tTf)); }
     CK(launch_attention(QKV, CTX, tT.segs, B, e.spT.maxlen, 12, r.s));
-    { ConvCall c; c.w = &e.att_dense; c.x = CTX; c.ldx = 768; c.y = TMP; c.ldy = 768; c.res = H; c.ldr = 768; RC(run_conv(r, c, tT)); }
+    { ConvCall c; c.w = &e.att_dense; c.x = CTX; c.ldx = 768; c.y = TMP; c.ldy = 768; c.res = H; c.ldr = 768; c.exact = true; RC(run_conv(r, c, tTf)); }
     CK(launch_layernorm(TMP, 768, nullptr, 0, A1, 768, R, 768, 1e-12f, 0, e.att_ln_g, e.att_ln_b, nullptr, 0, nullptr, ACT_NONE, 0.f, r.s));
-    { ConvCall c; c.w = &e.ffn; c.x = A1; c.ldx = 768; c.y = FF; c.ldy = 2048; c.act = ACT_GELU_NEW; RC(run_conv(r, c, tT)); }
-    { ConvCall c; c.w = &e.ffn_out; c.x = FF; c.ldx = 2048; c.y = TMP; c.ldy = 768; c.res = A1; c.ldr = 768; RC(run_conv(r, c, tT)); }
+    { ConvCall c; c.w = &e.ffn; c.x = A1; c.ldx = 768; c.y = FF; c.ldy = 2048; c.act = ACT_GELU_NEW; c.exact = true; RC(run_conv(r, c, tTf)); }
+    { ConvCall c; c.w = &e.ffn_out; c.x = FF; c.ldx = 2048; c.y = TMP; c.ldy = 768; c.res = A1; c.ldr = 768; c.exact = true; RC(run_conv(r, c, tTf)); }
     CK(launch_layernorm(TMP, 768, nullptr, 0, H, 768, R, 768, 1e-12f, 0, e.full_ln_g, e.full_ln_b, nullptr, 0, nullptr, ACT_NONE, 0.f, r.s));
   }
   RC(r.tap("bert", H, R, 768, 768));
@@ -761,11 +771,11 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   float* GX = r.alloc<float>((size_t)R * 2048);
   float* Y = r.alloc<float>((size_t)R * 512);
   if (!X || !GX || !Y) return TTSB_E_NOMEM;
-  { ConvCall c; c.w = &e.bert_enc; c.x = H; c.ldx = 768; c.y = X; c.ldy = 640; RC(run_conv(r, c, tT)); }
+  { ConvCall c; c.w = &e.bert_enc; c.x = H; c.ldx = 768; c.y = X; c.ldy = 640; c.exact = true; RC(run_conv(r, c, tTf)); }
   CK(launch_fill_style(d_ref, 256, 128, d_r2s, X, 640, 512, 128, R, r.s));
   RC(r.tap("d_en", X, R, 512, 640));
   for (int l = 0; l < 3; ++l) {
-    RC(run_bilstm(r, e.de_lstm[l], X, 640, GX, Y, 512, tT, d_ls, n_ls));
+    RC(run_bilstm(r, e.de_lstm[l], X, 640, GX, Y, 512, tTf, d_ls, n_ls, true));
     CK(launch_layernorm(Y, 512, nullptr, 0, X, 640, R, 512, 1e-5f, 1, nullptr, nullptr, e.d_gbP + e.de_aln[l].off, ldP, d_r2s, ACT_NONE, 0.f, r.s));
   }
   RC(r.tap("d", X, R, 640, 640));
@@ -778,8 +788,8 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   int* d_cum = r.alloc<int>(R);
   int* d_tot = r.alloc<int>(B);
   if (!logits || !d_dur || !d_pd || !d_cum || !d_tot) return TTSB_E_NOMEM;
-  RC(run_bilstm(r, e.dur_lstm, X, 640, GX, Y, 512, tT, d_lsq, n_ls));
-  { ConvCall c; c.w = &e.dur_proj; c.x = Y; c.ldx = 512; c.y = logits; c.ldy = 52; RC(run_conv(r, c, tT)); }
+  RC(run_bilstm(r, e.dur_lstm, X, 640, GX, Y, 512, tTf, d_lsq, n_ls, true));
+  { ConvCall c; c.w = &e.dur_proj; c.x = Y; c.ldx = 512; c.y = logits; c.ldy = 52; c.exact = true; RC(run_conv(r, c, tTf)); }
   CK(launch_duration(logits, 52, 50, d_r2s, d_speed, d_dur, d_pd, R, r.s));
   const int* d_used = d_forced ? d_forced : d_pd;
   CK(launch_dur_scan(d_used, tT.segs, B, d_cum, d_tot, r.s));
@@ -798,11 +808,11 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   if (!TE0 || !TE1 || !TEN) return TTSB_E_NOMEM;
   CK(launch_embedding(d_ids, e.te_emb, 512, TE0, 512, R, r.s));
   for (int l = 0; l < 3; ++l) {
-    ConvCall c; c.w = &e.te_cnn[l]; c.x = TE0; c.ldx = 512; c.y = TE1; c.ldy = 512; c.pad = 2;
+    ConvCall c; c.w = &e.te_cnn[l]; c.x = TE0; c.ldx = 512; c.y = TE1; c.ldy = 512; c.pad = 2; c.exact = true;
     RC(run_conv(r, c, tT));
     CK(launch_layernorm(TE1, 512, nullptr, 0, TE0, 512, R, 512, 1e-5f, 0, e.te_ln_g[l], e.te_ln_b[l], nullptr, 0, nullptr, ACT_LRELU, 0.2f, r.s));
   }
-  RC(run_bilstm(r, e.te_lstm, TE0, 512, GX, TEN, 512, tT, d_ls, n_ls));
+  RC(run_bilstm(r, e.te_lstm, TE0, 512, GX, TEN, 512, tTf, d_ls, n_ls, true));
   RC(r.tap("t_en", TEN, R, 512, 512));
   e.d_ten = TEN;
 
@@ -888,7 +898,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   float* F0 = r.alloc<float>(RL);
   float* NN = r.alloc<float>(RL);
   if (!GX || !SH || !st_sh || !F0 || !NN) return TTSB_E_NOMEM;
-  RC(run_bilstm(r, e.shared_lstm, EN, 640, GX, SH, 512, tF, d_lsF, (int)g_lsF.size()));
+  RC(run_bilstm(r, e.shared_lstm, EN, 640, GX, SH, 512, tF, d_lsF, (int)g_lsF.size(), false));
   CK(launch_colstats(SH, 512, 512, tF.segs, B, st_sh, 512, r.s));
   for (int br = 0; br < 2; ++br) {
     const ResBlk1dW* blk = br == 0 ? e.f0_blk : e.n_blk;

@@ -21,7 +21,9 @@ struct ConvW {
   float* bias = nullptr;                  // [Cout] or null
   uint16_t* wb = nullptr;                 // bf16 UMMA pack (see conv_umma.cu), or null
   uint16_t* wh = nullptr;                 // fp16 UMMA pack, or null
+  uint16_t* ws = nullptr;                 // split-fp16 UMMA pack (hi | lo), or null: fp32-equivalent tensor-core path
   int cin_pad = 0, cout_pad = 0;
+  int cin_pad_s = 0, cout_pad_s = 0;
   int Cin = 0, Cout = 0, k = 1;
 };
 struct LstmW {

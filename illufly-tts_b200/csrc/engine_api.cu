@@ -329,7 +329,7 @@ int ttsb_op_conv1d(ttsb_engine* h, const float* x, const float* w, const float* 
       for (int j = 0; j < k; ++j) p[((size_t)j * Cin + ci) * ldw + co] = w[((size_t)co * Cin + ci) * k + j];
   std::vector<uint16_t> pb;
   int cin_pad = 0, cout_pad = 0;
-  const int wfmt = precision == TTSB_PRECISION_FP16 ? 1 : 0;
+  const int wfmt = precision == 3 ? 2 : (precision == TTSB_PRECISION_FP16 ? 1 : 0);      // 3: split-fp16 (test hook)
   pack_umma_weights(p.data(), k, Cin, Cout, ldw, wfmt, pb, cin_pad, cout_pad);
   float* dw = (float*)e.arena.alloc(sizeof(float) * p.size());
   uint16_t* dwb = (uint16_t*)e.arena.alloc(sizeof(uint16_t) * std::max<size_t>(pb.size(), 8));
