@@ -133,6 +133,9 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// PRO (fused operand prologue) and WFMT (operand format) are compile-time: the producers' per-element code is the
+// instruction-issue hot spot of the kernel (ncu), so no run-time switches inside it.
+template <int PRO, int WFMT>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& p = u.a;
@@ -187,7 +190,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     for (int item = item0; item < item1; ++item) {
       const Tile tile = p.tiles[item % p.ntiles];
       const Seg seg = p.segs[tile.seg];
-      if (p.pro >= PRO_ADAIN_LRELU && tile.seg != cur_seg) {
+      if (PRO >= PRO_ADAIN_LRELU && tile.seg != cur_seg) {
         // per-(utterance, channel) AdaIN coefficients; only producers read them, so a producer-only barrier suffices
         asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
         for (int c = tid; c < cpad; c += NPROD) {
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           if (c < p.Cin) {
             const double* st = p.pstats + ((size_t)tile.seg * p.ld_pstats + c) * 2;
             adain_coef(st, seg.in_len, p.gb[(size_t)tile.seg * p.ld_gb + c], p.gb[(size_t)tile.seg * p.ld_gb + p.beta_off + c], mean, a, b);
-            if (p.pro == PRO_ADAIN_SNAKE) al = p.alpha[c];
+            if (PRO == PRO_ADAIN_SNAKE) al = p.alpha[c];
           }
           s_par[c] = mean; s_par[cpad + c] = a; s_par[2 * cpad + c] = b; s_par[3 * cpad + c] = al; s_par[4 * cpad + c] = 1.0f / al;
         }
@@ -207,23 +210,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         mbar_wait(bar_slab_empty(b), ((g >> 1) & 1u) ^ 1u);
         const int c0 = sc * pl.KS + pln * 8;
         float pm[8], pa[8], pb[8], pal[8], pia[8];
-        if (p.pro >= PRO_ADAIN_LRELU) {
+        if (PRO >= PRO_ADAIN_LRELU) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             pm[e] = s_par[c0 + e]; pa[e] = s_par[cpad + c0 + e]; pb[e] = s_par[2 * cpad + c0 + e];
-            pal[e] = s_par[3 * cpad + c0 + e]; pia[e] = s_par[4 * cpad + c0 + e];
+            if (PRO == PRO_ADAIN_SNAKE) { pal[e] = s_par[3 * cpad + c0 + e]; pia[e] = s_par[4 * cpad + c0 + e]; }
           }
         }
+        const bool tailc = c0 + 8 > p.Cin;                 // only the last channel chunk needs per-element masking
         uint8_t* slab = smem + pl.off_slab + (size_t)b * pl.slab_bytes + (size_t)pln * pl.SR * 16;
         const size_t lo_off = (size_t)planes * pl.SR * 16;      // split mode: the low halves follow the high planes
         const bool second = c0 + 4 < p.ldx;
-        // two rows per iteration: four 16-B loads in flight per thread before any arithmetic
-        for (int r = r0; r < pl.SR; r += 2 * rpp) {
-          float v[2][8];
-          bool ok[2];
+        // software-pipelined batches of 4 rows: the eight 16-B loads of batch n+1 are in flight while batch n is transformed
+        // (ncu: the producer was stalled on long_scoreboard right after its loads; 1 CTA/SM leaves no other warps to hide it)
+        auto load_batch = [&](int rbase, float (&v)[4][8], bool (&ok)[4]) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int rr = r + h * rpp;
+          for (int h = 0; h < 4; ++h) {
+            const int rr = rbase + h * rpp;
             const int traw = tile.t0 + rr - p.pad;
             const int tin = traw >> p.in_shr;
             ok[h] = rr < pl.SR && traw >= 0 && tin < seg.in_len && c0 < p.Cin;
@@ -239,26 +242,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
               }
             }
           }
+        };
+        auto finish_batch = [&](int rbase, float (&v)[4][8], const bool (&ok)[4]) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int rr = r + h * rpp;
+          for (int h = 0; h < 4; ++h) {
+            const int rr = rbase + h * rpp;
             if (rr >= pl.SR) break;
             if (ok[h]) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 float x = v[h][e];
-                if (p.pro == PRO_LRELU) x = lrelu(x, p.slope);
-                else if (p.pro == PRO_ADAIN_LRELU) x = lrelu(fmaf(x - pm[e], pa[e], pb[e]), p.slope);
-                else if (p.pro == PRO_ADAIN_SNAKE) {
+                if (PRO == PRO_LRELU) x = lrelu(x, p.slope);
+                else if (PRO == PRO_ADAIN_LRELU) x = lrelu(fmaf(x - pm[e], pa[e], pb[e]), p.slope);
+                else if (PRO == PRO_ADAIN_SNAKE) {
                   const float wv = fmaf(x - pm[e], pa[e], pb[e]);
                   const float sn = __sinf(pal[e] * wv);
                   x = fmaf(pia[e], sn * sn, wv);
                 }
-                v[h][e] = (c0 + e < p.Cin) ? x : 0.f;
+                v[h][e] = x;
+              }
+              if (tailc) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) if (c0 + e >= p.Cin) v[h][e] = 0.f;
               }
             }
             uint4 o;
-            if (p.wfmt == 2) {
+            if (WFMT == 2) {
               uint4 ol;
               float hi[8], lo[8];
 #pragma unroll
@@ -271,9 +280,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
               ol.x = pack_f16(lo[0], lo[1]); ol.y = pack_f16(lo[2], lo[3]); ol.z = pack_f16(lo[4], lo[5]); ol.w = pack_f16(lo[6], lo[7]);
               *reinterpret_cast<uint4*>(slab + lo_off + (size_t)rr * 16) = ol;
             }
-            else if (p.wfmt == 1) { o.x = pack_f16(v[h][0], v[h][1]); o.y = pack_f16(v[h][2], v[h][3]); o.z = pack_f16(v[h][4], v[h][5]); o.w = pack_f16(v[h][6], v[h][7]); }
+            else if (WFMT == 1) { o.x = pack_f16(v[h][0], v[h][1]); o.y = pack_f16(v[h][2], v[h][3]); o.z = pack_f16(v[h][4], v[h][5]); o.w = pack_f16(v[h][6], v[h][7]); }
             else { o.x = pack_bf16(v[h][0], v[h][1]); o.y = pack_bf16(v[h][2], v[h][3]); o.z = pack_bf16(v[h][4], v[h][5]); o.w = pack_bf16(v[h][6], v[h][7]); }
             *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
+          }
+        };
+        {
+          float va[4][8];
+          bool oka[4];
+          for (int r = r0; r < pl.SR; r += 4 * rpp) {
+            load_batch(r, va, oka);
+            finish_batch(r, va, oka);
           }
         }
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
@@ -302,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   } else if (warp == NPW + 1) {
     // =================== MMA issuer ===================
     if (lane == 0) {
-      const uint32_t ofmt = p.wfmt >= 1 ? 0u : 1u;     // instruction-descriptor operand format: 0 = F16, 1 = BF16
+      const uint32_t ofmt = WFMT >= 1 ? 0u : 1u;       // instruction-descriptor operand format: 0 = F16, 1 = BF16
       const uint32_t a_lo = (uint32_t)(pl.KS >> 3) * (uint32_t)pl.SR * 16u;     // split mode: offset of the low-half planes
       const uint32_t b_lo = (uint32_t)pl.BN * KCH * 2u;                         //             and of the low-half weight block
       const uint32_t idesc = (1u << 4) | (ofmt << 7) | (ofmt << 10) | ((uint32_t)(pl.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -332,7 +349,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
                 const uint32_t aaddr = sbase + (uint32_t)(((kc * 8 + kk * 2) * pl.SR + j * p.dil) * 16);
                 const uint32_t baddr = wbase + (uint32_t)(kk * 2 * pl.BN * 16);
                 umma_bf16(tacc, make_desc(aaddr, a_lbo, a_sbo), make_desc(baddr, b_lbo, b_sbo), idesc, first ? 0u : 1u);
-                if (pl.split) {
+                if (WFMT == 2) {
                   // x w ~= xh wh + (xh wl + xl wh)   (xl wl is ~2^-22 relative and dropped).  The tensor core truncates at
                   // every accumulate, an error that grows linearly with the number of MMAs into one accumulator: the cross
                   // terms (2^-11 of the main term) go to their own accumulator, so the main one sees K/16 steps, not 3K/16
@@ -371,7 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         const int co = n0 + c0 + cc;
         uint32_t v[32];
         tmem_ld32(tacc + (uint32_t)c0, v);
-        if (pl.split) {
+        if (WFMT == 2) {
           uint32_t v2[32];
           tmem_ld32(tacc + (uint32_t)(pl.BN + c0), v2);
 #pragma unroll
@@ -589,12 +606,23 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   u.a = a;
   if (!make_plan(a, u.p)) return cudaErrorInvalidValue;
   if (a.wfmt == 2) u.a.acc_scale = 1.0f / (SPLIT_SA * SPLIT_SW);
+  using KernelFn = void (*)(const UArgs);
+  static const KernelFn table[4][3] = {
+      {conv_umma_kernel<PRO_NONE, 0>, conv_umma_kernel<PRO_NONE, 1>, conv_umma_kernel<PRO_NONE, 2>},
+      {conv_umma_kernel<PRO_LRELU, 0>, conv_umma_kernel<PRO_LRELU, 1>, conv_umma_kernel<PRO_LRELU, 2>},
+      {conv_umma_kernel<PRO_ADAIN_LRELU, 0>, conv_umma_kernel<PRO_ADAIN_LRELU, 1>, conv_umma_kernel<PRO_ADAIN_LRELU, 2>},
+      {conv_umma_kernel<PRO_ADAIN_SNAKE, 0>, conv_umma_kernel<PRO_ADAIN_SNAKE, 1>, conv_umma_kernel<PRO_ADAIN_SNAKE, 2>}};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 3; ++j) {
+        cudaError_t e = cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+      }
     attr_set = true;
   }
+  if (a.pro < 0 || a.pro > 3 || a.wfmt < 0 || a.wfmt > 2) return cudaErrorInvalidValue;
+  const KernelFn kernel = table[a.pro][a.wfmt];
   if (g_num_sms == 0) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -605,7 +633,7 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   const int ncta = u.p.items < g_num_sms ? u.p.items : g_num_sms;      // persistent: one CTA per SM
   u.p.per_cta = (u.p.items + ncta - 1) / ncta;
   const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
-  conv_umma_kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
+  kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
   return launched();
 }
 
