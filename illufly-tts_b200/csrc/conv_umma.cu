@@ -19,6 +19,9 @@
 // Reference maths: SURVEY.md A.7, A.11, A.12 (kokoro AdainResBlk1d / Generator / AdaINResBlock1).
 #include "common.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 namespace ttsb {
 
 namespace {
@@ -44,6 +47,9 @@ struct Plan {
 struct UArgs {
   ConvArgs a;
   Plan p;
+  long long* prof;   // optional [grid][16] cycle counters per role (TTSB_UMMA_PROF), else null
+  int dbg;     // TTSB_UMMA_DBG (timing experiments only, results become garbage): 1 = producers skip global loads,
+               // 2 = epilogue skips global traffic, 4 = no MMA issue; applied to the Snake-prologue variants only
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------
@@ -72,6 +78,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > SPIN_LIMIT) __trap();
   }
+}
+// timed variant for the role profile (cycles spent waiting are added to *acc)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
@@ -125,11 +137,48 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ uint32_t pack_f16_nosat(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   lo = fminf(fmaxf(lo, -65504.f), 65504.f);     // saturate instead of producing inf
   hi = fminf(fmaxf(hi, -65504.f), 65504.f);
   __half2 t = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+
+
+// One 32-row x 32-column chunk of the epilogue for a warp, fast path: the tile is fully inside the utterance, the channel
+// group is complete, no activation.  y = (acc * acs + bias [+ res]) [* os] [+ y_old]; returns the lane's partial column sums.
+// RES / SCALE / ACC are compile-time so that each launch runs one short loop (4 epilogue warps are issue-latency bound:
+// ncu shows ~8 cycles per instruction per warp, so the instruction count per element is what matters).
+template <bool RES, bool SCALE, bool ACC>
+__device__ __forceinline__ void epi_chunk_fast(const float* __restrict__ stg, int lane, float acs, float os, const float4 b4, float* __restrict__ yb,
+                                               size_t ystep, const float* __restrict__ rb, size_t rstep, float (&ps)[4], float (&pq)[4]) {
+  float4 r4[8], y4[8];
+  if (RES) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(rb + i * rstep);
+  }
+  if (ACC) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y4[i] = *reinterpret_cast<const float4*>(yb + i * ystep);
+  }
+  const float* sp = stg + (lane >> 3) * STG_LD + (lane & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a4 = *reinterpret_cast<const float4*>(sp + i * 4 * STG_LD);
+    float4 o;
+    o.x = fmaf(a4.x, acs, b4.x); o.y = fmaf(a4.y, acs, b4.y); o.z = fmaf(a4.z, acs, b4.z); o.w = fmaf(a4.w, acs, b4.w);
+    if (RES) { o.x += r4[i].x; o.y += r4[i].y; o.z += r4[i].z; o.w += r4[i].w; }
+    if (SCALE && ACC) { o.x = fmaf(o.x, os, y4[i].x); o.y = fmaf(o.y, os, y4[i].y); o.z = fmaf(o.z, os, y4[i].z); o.w = fmaf(o.w, os, y4[i].w); }
+    else if (SCALE) { o.x *= os; o.y *= os; o.z *= os; o.w *= os; }
+    else if (ACC) { o.x += y4[i].x; o.y += y4[i].y; o.z += y4[i].z; o.w += y4[i].w; }
+    *reinterpret_cast<float4*>(yb + i * ystep) = o;
+    ps[0] += o.x; ps[1] += o.y; ps[2] += o.z; ps[3] += o.w;
+    pq[0] = fmaf(o.x, o.x, pq[0]); pq[1] = fmaf(o.y, o.y, pq[1]); pq[2] = fmaf(o.z, o.z, pq[2]); pq[3] = fmaf(o.w, o.w, pq[3]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -187,6 +236,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     const int pln = tid % planes, r0 = tid / planes;
     int cur_seg = -1;
     uint32_t g = 0;                                    // running slab counter of this CTA
+    long long t_wait = 0;
+    const long long t_start = clock64();
     for (int item = item0; item < item1; ++item) {
       const Tile tile = p.tiles[item % p.ntiles];
       const Seg seg = p.segs[tile.seg];
@@ -200,21 +251,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             adain_coef(st, seg.in_len, p.gb[(size_t)tile.seg * p.ld_gb + c], p.gb[(size_t)tile.seg * p.ld_gb + p.beta_off + c], mean, a, b);
             if (PRO == PRO_ADAIN_SNAKE) al = p.alpha[c];
           }
-          s_par[c] = mean; s_par[cpad + c] = a; s_par[2 * cpad + c] = b; s_par[3 * cpad + c] = al; s_par[4 * cpad + c] = 1.0f / al;
+          // folded constants: AdaIN is one FFMA  w = x A + B  (A = (1+gamma) rstd, B = beta - mean A);
+          // Snake  w + sin^2(alpha w)/alpha = (w + k) - k cos(2 alpha w),  k = 1/(2 alpha):  wk = x A + (B + k),  t = x (2 alpha A) + 2 alpha B
+          const float Bf = fmaf(-mean, a, b);
+          const float kk = 0.5f / al;
+          s_par[c] = a; s_par[cpad + c] = (PRO == PRO_ADAIN_SNAKE) ? Bf + kk : Bf;
+          s_par[2 * cpad + c] = 2.f * al * a; s_par[3 * cpad + c] = 2.f * al * Bf; s_par[4 * cpad + c] = kk;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
         cur_seg = tile.seg;
       }
       for (int sc = 0; sc < pl.nsc; ++sc, ++g) {
         const uint32_t b = g & 1u;
-        mbar_wait(bar_slab_empty(b), ((g >> 1) & 1u) ^ 1u);
+        mbar_wait_t(bar_slab_empty(b), ((g >> 1) & 1u) ^ 1u, t_wait);
         const int c0 = sc * pl.KS + pln * 8;
-        float pm[8], pa[8], pb[8], pal[8], pia[8];
+        float pA[8], pB[8], pA2[8], pB2[8], pK[8];
         if (PRO >= PRO_ADAIN_LRELU) {
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            pm[e] = s_par[c0 + e]; pa[e] = s_par[cpad + c0 + e]; pb[e] = s_par[2 * cpad + c0 + e];
-            if (PRO == PRO_ADAIN_SNAKE) { pal[e] = s_par[3 * cpad + c0 + e]; pia[e] = s_par[4 * cpad + c0 + e]; }
+            pA[e] = s_par[c0 + e]; pB[e] = s_par[cpad + c0 + e];
+            if (PRO == PRO_ADAIN_SNAKE) { pA2[e] = s_par[2 * cpad + c0 + e]; pB2[e] = s_par[3 * cpad + c0 + e]; pK[e] = s_par[4 * cpad + c0 + e]; }
           }
         }
         const bool tailc = c0 + 8 > p.Cin;                 // only the last channel chunk needs per-element masking
@@ -223,13 +279,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         const bool second = c0 + 4 < p.ldx;
         // software-pipelined batches of 4 rows: the eight 16-B loads of batch n+1 are in flight while batch n is transformed
         // (ncu: the producer was stalled on long_scoreboard right after its loads; 1 CTA/SM leaves no other warps to hide it)
-        auto load_batch = [&](int rbase, float (&v)[4][8], bool (&ok)[4]) {
+        constexpr int NB = 2;        // rows per batch (two batches live in registers)
+        auto load_batch = [&](int rbase, float (&v)[NB][8], bool (&ok)[NB]) {
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
+          for (int h = 0; h < NB; ++h) {
             const int rr = rbase + h * rpp;
             const int traw = tile.t0 + rr - p.pad;
             const int tin = traw >> p.in_shr;
-            ok[h] = rr < pl.SR && traw >= 0 && tin < seg.in_len && c0 < p.Cin;
+            ok[h] = rr < pl.SR && traw >= 0 && tin < seg.in_len && c0 < p.Cin && !(u.dbg & 1);
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[h][e] = 0.f;
             if (ok[h]) {
@@ -243,22 +300,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             }
           }
         };
-        auto finish_batch = [&](int rbase, float (&v)[4][8], const bool (&ok)[4]) {
+        auto finish_batch = [&](int rbase, float (&v)[NB][8], const bool (&ok)[NB]) {
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
+          for (int h = 0; h < NB; ++h) {
             const int rr = rbase + h * rpp;
             if (rr >= pl.SR) break;
             if (ok[h]) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 float x = v[h][e];
-                if (PRO == PRO_LRELU) x = lrelu(x, p.slope);
-                else if (PRO == PRO_ADAIN_LRELU) x = lrelu(fmaf(x - pm[e], pa[e], pb[e]), p.slope);
-                else if (PRO == PRO_ADAIN_SNAKE) {
-                  const float wv = fmaf(x - pm[e], pa[e], pb[e]);
-                  const float sn = __sinf(pal[e] * wv);
-                  x = fmaf(pia[e], sn * sn, wv);
-                }
+                if (PRO == PRO_LRELU) x = fmaxf(x, x * p.slope);                    // slope < 1
+                else if (PRO == PRO_ADAIN_LRELU) { const float wv = fmaf(x, pA[e], pB[e]); x = fmaxf(wv, wv * p.slope); }
+                else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-pK[e], __cosf(fmaf(x, pA2[e], pB2[e])), fmaf(x, pA[e], pB[e]));
                 v[h][e] = x;
               }
               if (tailc) {
@@ -280,23 +333,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
               ol.x = pack_f16(lo[0], lo[1]); ol.y = pack_f16(lo[2], lo[3]); ol.z = pack_f16(lo[4], lo[5]); ol.w = pack_f16(lo[6], lo[7]);
               *reinterpret_cast<uint4*>(slab + lo_off + (size_t)rr * 16) = ol;
             }
-            else if (WFMT == 1) { o.x = pack_f16(v[h][0], v[h][1]); o.y = pack_f16(v[h][2], v[h][3]); o.z = pack_f16(v[h][4], v[h][5]); o.w = pack_f16(v[h][6], v[h][7]); }
+            else if (WFMT == 1) {
+              if (PRO >= PRO_ADAIN_LRELU) {      // instance-normalised data is bounded (|x^| <= sqrt(n)): no saturation needed
+                o.x = pack_f16_nosat(v[h][0], v[h][1]); o.y = pack_f16_nosat(v[h][2], v[h][3]); o.z = pack_f16_nosat(v[h][4], v[h][5]); o.w = pack_f16_nosat(v[h][6], v[h][7]);
+              } else {
+                o.x = pack_f16(v[h][0], v[h][1]); o.y = pack_f16(v[h][2], v[h][3]); o.z = pack_f16(v[h][4], v[h][5]); o.w = pack_f16(v[h][6], v[h][7]);
+              }
+            }
             else { o.x = pack_bf16(v[h][0], v[h][1]); o.y = pack_bf16(v[h][2], v[h][3]); o.z = pack_bf16(v[h][4], v[h][5]); o.w = pack_bf16(v[h][6], v[h][7]); }
             *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
           }
         };
         {
-          float va[4][8];
-          bool oka[4];
-          for (int r = r0; r < pl.SR; r += 4 * rpp) {
-            load_batch(r, va, oka);
+          // ping-pong: the loads of batch n+1 are issued before batch n is transformed
+          float va[NB][8], vb[NB][8];
+          bool oka[NB], okb[NB];
+          const int step = NB * rpp;
+          int r = r0;
+          load_batch(r, va, oka);
+          for (;;) {
+            if (r + step < pl.SR) load_batch(r + step, vb, okb);
             finish_batch(r, va, oka);
+            r += step;
+            if (r >= pl.SR) break;
+            if (r + step < pl.SR) load_batch(r + step, va, oka);
+            finish_batch(r, vb, okb);
+            r += step;
+            if (r >= pl.SR) break;
           }
         }
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
         mbar_arrive(bar_slab_full(b));
       }
     }
+    if (u.prof && tid == 0) { u.prof[blockIdx.x * 16 + 0] = clock64() - t_start; u.prof[blockIdx.x * 16 + 1] = t_wait; }
   } else if (warp == NPW) {
     // =================== weight loader (bulk-copy engine) ===================
     if (lane == 0) {
@@ -325,36 +395,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       const uint32_t idesc = (1u << 4) | (ofmt << 7) | (ofmt << 10) | ((uint32_t)(pl.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_lbo = (uint32_t)pl.SR * 16u, a_sbo = 128u;
       const uint32_t b_lbo = (uint32_t)pl.BN * 16u, b_sbo = 128u;
+      const uint64_t a_desc0 = make_desc(0, a_lbo, a_sbo), b_desc0 = make_desc(0, b_lbo, b_sbo);
+      const uint32_t a_kstep = (uint32_t)(2 * pl.SR);          // two 16-B channel planes per K=16 step, in 16-B units
+      const uint32_t b_kstep = (uint32_t)(2 * pl.BN);
       uint32_t it = 0, g = 0, n = 0;
+      long long tw_slab = 0, tw_acc = 0, tw_w = 0;
+      const long long t_start = clock64();
       for (int item = item0; item < item1; ++item, ++n) {
         const uint32_t slot = n & 1u;
-        mbar_wait(bar_acc_empty(slot), ((n >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
+        mbar_wait_t(bar_acc_empty(slot), ((n >> 1) & 1u) ^ 1u, tw_acc);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tacc = tmem_base + slot * (uint32_t)pl.acc_cols;
         const uint32_t tcor = tacc + (uint32_t)pl.BN;       // split mode: the small cross terms get their own accumulator
         uint32_t first = 1;
         for (int sc = 0; sc < pl.nsc; ++sc, ++g) {
           const uint32_t b = g & 1u;
-          mbar_wait(bar_slab_full(b), (g >> 1) & 1u);
+          mbar_wait_t(bar_slab_full(b), (g >> 1) & 1u, tw_slab);
           tc_fence_after();
           const uint32_t sbase = slab0 + b * pl.slab_bytes;
           for (int j = 0; j < p.k; ++j)
             for (int kc = 0; kc < nwst; ++kc, ++it) {
               const uint32_t s = it % NS;
-              mbar_wait(bar_full(s), (it / NS) & 1u);
+              mbar_wait_t(bar_full(s), (it / NS) & 1u, tw_w);
               tc_fence_after();
               const uint32_t wbase = w0 + s * pl.wstage_bytes;
+              // descriptors differ only in the 14-bit start-address field (address >> 4): one 64-bit add per operand per MMA.
+              // (The issuing thread's own instruction latency bounds the MMA rate: measured 960 cycles per 4-MMA stage with
+              //  the descriptors rebuilt from scratch, against 256 cycles of tensor-core time.)
+              const uint64_t ad0 = a_desc0 + (uint64_t)((sbase >> 4) + (uint32_t)(kc * 8 * pl.SR + j * p.dil));
+              const uint64_t bd0 = b_desc0 + (uint64_t)(wbase >> 4);
 #pragma unroll
               for (int kk = 0; kk < KCH / 16; ++kk) {
-                const uint32_t aaddr = sbase + (uint32_t)(((kc * 8 + kk * 2) * pl.SR + j * p.dil) * 16);
-                const uint32_t baddr = wbase + (uint32_t)(kk * 2 * pl.BN * 16);
-                umma_bf16(tacc, make_desc(aaddr, a_lbo, a_sbo), make_desc(baddr, b_lbo, b_sbo), idesc, first ? 0u : 1u);
+                const uint64_t ad = ad0 + (uint64_t)(kk * a_kstep);
+                const uint64_t bd = bd0 + (uint64_t)(kk * b_kstep);
+                if (!(u.dbg & 4)) umma_bf16(tacc, ad, bd, idesc, first ? 0u : 1u);
                 if (WFMT == 2) {
                   // x w ~= xh wh + (xh wl + xl wh)   (xl wl is ~2^-22 relative and dropped).  The tensor core truncates at
                   // every accumulate, an error that grows linearly with the number of MMAs into one accumulator: the cross
                   // terms (2^-11 of the main term) go to their own accumulator, so the main one sees K/16 steps, not 3K/16
-                  umma_bf16(tcor, make_desc(aaddr, a_lbo, a_sbo), make_desc(baddr + b_lo, b_lbo, b_sbo), idesc, first ? 0u : 1u);
-                  umma_bf16(tcor, make_desc(aaddr + a_lo, a_lbo, a_sbo), make_desc(baddr, b_lbo, b_sbo), idesc, 1u);
+                  umma_bf16(tcor, ad, bd + (uint64_t)(b_lo >> 4), idesc, first ? 0u : 1u);
+                  umma_bf16(tcor, ad + (uint64_t)(a_lo >> 4), bd, idesc, 1u);
                 }
                 first = 0;
               }
@@ -363,6 +443,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           umma_commit(bar_slab_empty(b));           // slab free once every MMA issued so far has completed
         }
         umma_commit(bar_acc_full(slot));            // accumulator of this item complete
+      }
+      if (u.prof) {
+        long long* pp = u.prof + blockIdx.x * 16;
+        pp[2] = clock64() - t_start; pp[3] = tw_slab; pp[4] = tw_acc; pp[5] = tw_w;
       }
     }
   } else {
@@ -374,13 +458,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     const int cc = (lane & 7) * 4;
     const float acs = p.acc_scale != 0.f ? p.acc_scale : 1.0f;
     uint32_t n = 0;
+    long long tw_full = 0;
+    const long long t_start = clock64();
     for (int item = item0; item < item1; ++item, ++n) {
       const int nt = item / p.ntiles;
       const Tile tile = p.tiles[item % p.ntiles];
       const Seg seg = p.segs[tile.seg];
       const int n0 = nt * pl.BN;
       const uint32_t slot = n & 1u;
-      mbar_wait(bar_acc_full(slot), (n >> 1) & 1u);
+      mbar_wait_t(bar_acc_full(slot), (n >> 1) & 1u, tw_full);
       tc_fence_after();
       const uint32_t tacc = tmem_base + slot * (uint32_t)pl.acc_cols + ((uint32_t)(q * 32) << 16);
       for (int chunk = 0; chunk < nchunk; ++chunk) {
@@ -406,9 +492,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         }
         __syncwarp();
         float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
-        const bool colok = co < p.Cout;
+        const bool colok = co < p.Cout && !(u.dbg & 2);
         const bool full4 = co + 3 < p.Cout;
-        if (colok && full4) {
+        if (colok && full4 && tile.t0 + BM <= seg.out_len && p.act == ACT_NONE) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + co);
+          const size_t row0 = (size_t)(seg.out_off + tile.t0 + q * 32 + (lane >> 3));
+          float* yb = p.y + row0 * p.ldy + co;
+          const size_t ystep = (size_t)4 * p.ldy, rstep = (size_t)4 * p.ldr;
+          const float* rb = p.res ? p.res + row0 * p.ldr + co : nullptr;
+          const bool sc = p.out_scale != 1.0f;
+          if (p.res && p.accumulate) epi_chunk_fast<true, true, true>(stg, lane, acs, p.out_scale, b4, yb, ystep, rb, rstep, ps, pq);
+          else if (p.res && sc) epi_chunk_fast<true, true, false>(stg, lane, acs, p.out_scale, b4, yb, ystep, rb, rstep, ps, pq);
+          else if (p.res) epi_chunk_fast<true, false, false>(stg, lane, acs, 1.f, b4, yb, ystep, rb, rstep, ps, pq);
+          else if (p.accumulate) epi_chunk_fast<false, true, true>(stg, lane, acs, p.out_scale, b4, yb, ystep, rb, rstep, ps, pq);
+          else if (sc) epi_chunk_fast<false, true, false>(stg, lane, acs, p.out_scale, b4, yb, ystep, rb, rstep, ps, pq);
+          else epi_chunk_fast<false, false, false>(stg, lane, acs, 1.f, b4, yb, ystep, rb, rstep, ps, pq);
+        } else if (colok && full4) {
           // all global reads of the chunk first (res / y may alias the output, so the compiler cannot hoist them itself)
           float4 r4[8], y4[8];
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -441,14 +541,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             }
           }
         } else if (colok) {
-#pragma unroll
+          // ragged last channel group (Cout % 4 != 0): compact scalar loop, deliberately not unrolled (instruction cache)
+#pragma unroll 1
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + (lane >> 3);
             const int t = tile.t0 + q * 32 + rr;
             if (t < seg.out_len) {
               const size_t orow = (size_t)(seg.out_off + t);
               float* dst = p.y + orow * p.ldy + co;
-#pragma unroll
+#pragma unroll 1
               for (int e = 0; e < 4; ++e) {
                 if (co + e < p.Cout) {
                   float xv = stg[rr * STG_LD + cc + e] * acs;
@@ -458,7 +559,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
                   xv *= p.out_scale;
                   if (p.accumulate) xv += dst[e];
                   dst[e] = xv;
-                  ps[e] += xv; pq[e] += xv * xv;
+                  if (e == 0) { ps[0] += xv; pq[0] += xv * xv; }
+                  else if (e == 1) { ps[1] += xv; pq[1] += xv * xv; }
+                  else if (e == 2) { ps[2] += xv; pq[2] += xv * xv; }
+                  else { ps[3] += xv; pq[3] += xv * xv; }
                 }
               }
             }
@@ -502,6 +606,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       }
     }
     tc_fence_before();
+    if (u.prof && et == 0) { u.prof[blockIdx.x * 16 + 6] = clock64() - t_start; u.prof[blockIdx.x * 16 + 7] = tw_full; u.prof[blockIdx.x * 16 + 8] = item1 - item0; }
   }
   __syncthreads();
   if (warp == NPW + 1) tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
@@ -622,6 +727,16 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   if (a.pro < 0 || a.pro > 3 || a.wfmt < 0 || a.wfmt > 2) return cudaErrorInvalidValue;
+  static int dbg = -1;
+  if (dbg < 0) { const char* ev = getenv("TTSB_UMMA_DBG"); dbg = ev ? atoi(ev) : 0; }
+  u.dbg = a.pro == PRO_ADAIN_SNAKE ? dbg : 0;
+  static int prof_on = -1;
+  static long long* prof_buf = nullptr;
+  if (prof_on < 0) {
+    prof_on = getenv("TTSB_UMMA_PROF") ? 1 : 0;
+    if (prof_on && cudaMalloc(&prof_buf, sizeof(long long) * 16 * 256) != cudaSuccess) prof_on = 0;
+  }
+  u.prof = prof_on ? prof_buf : nullptr;
   const KernelFn kernel = table[a.pro][a.wfmt];
   if (g_num_sms == 0) {
     int dev = 0;
@@ -634,6 +749,15 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   u.p.per_cta = (u.p.items + ncta - 1) / ncta;
   const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
   kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
+  if (prof_on) {      // diagnostic mode: synchronous, prints the mean cycle split of the roles for every launch
+    static long long host[16 * 256];
+    if (cudaStreamSynchronize(s) == cudaSuccess && cudaMemcpy(host, prof_buf, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      double m[9] = {0};
+      for (int c = 0; c < grid; ++c) for (int i = 0; i < 9; ++i) m[i] += (double)host[c * 16 + i] / grid;
+      fprintf(stderr, "umma pro=%d fmt=%d Cin=%d Cout=%d k=%d dil=%d grid=%d items/cta=%.1f | producer %.0f (wait %.0f) | mma %.0f (wait slab %.0f acc %.0f w %.0f) | epilogue %.0f (wait %.0f) cycles\n",
+              a.pro, a.wfmt, a.Cin, a.Cout, a.k, a.dil, grid, m[8], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+    }
+  }
   return launched();
 }
 

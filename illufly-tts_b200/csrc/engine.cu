@@ -330,6 +330,24 @@ int engine_finalize(Engine& e) {
   e.src_lin_w = ld.upload_named(G + "m_source.l_linear.weight");
   e.src_lin_b = ld.upload_named(G + "m_source.l_linear.bias");
   ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, 1) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, 1);
+  if (ok) {
+    // noise_convs[0]: Conv1d(22, 256, k12, stride 6, pad 3) over STFT frames == k3/pad1 conv over frames regrouped six at a time
+    // ([blocks, 6 x 24] view of the channels-last har buffer): tap in {0,1,2}, slot i in 0..5  <->  original tap j = 6 tap + i - 3
+    const HostTensor* w0 = ld.get(G + "noise_convs.0.weight");
+    const HostTensor* b0 = ld.get(G + "noise_convs.0.bias");
+    if (w0 && b0 && w0->shape.size() == 3 && w0->shape[1] == 22 && w0->shape[2] == 12) {
+      const int Co = (int)w0->shape[0];
+      HostTensor wr; wr.shape = {Co, 144, 3}; wr.data.assign((size_t)Co * 144 * 3, 0.f);
+      for (int co = 0; co < Co; ++co)
+        for (int tap = 0; tap < 3; ++tap)
+          for (int i = 0; i < 6; ++i) {
+            const int j = 6 * tap + i - 3;
+            if (j < 0 || j >= 12) continue;
+            for (int c = 0; c < 22; ++c) wr.data[((size_t)co * 144 + i * 24 + c) * 3 + tap] = w0->data[((size_t)co * 22 + c) * 12 + j];
+          }
+      ld.pack_conv(wr, &b0->data, e.noise_conv0r, 1);
+    } else ok = false;
+  }
   ok = ok && pack_convT(ld, G + "ups.0", 10, e.ups[0]) && pack_convT(ld, G + "ups.1", 6, e.ups[1]);
   ok = ok && ld.resblock1(G + "noise_res.0", e.noise_res[0], 256, 7, swD, sbD) && ld.resblock1(G + "noise_res.1", e.noise_res[1], 128, 11, swD, sbD);
   const int rk[3] = {3, 7, 11};
@@ -400,6 +418,19 @@ struct Run {
     t.out_rows = out.total * out_scale; t.in_rows = in.total * in_scale;
     return t;
   }
+  SegTab make_tab_segs(const std::vector<Seg>& segs, bool want_tiles = true, int tile_rows = 128) {
+    std::vector<Tile> tiles;
+    SegTab t;
+    for (int b = 0; b < (int)segs.size(); ++b) {
+      if (want_tiles)
+        for (int t0 = 0; t0 < segs[b].out_len; t0 += tile_rows) tiles.push_back({b, t0});
+      t.max_out = std::max(t.max_out, segs[b].out_len); t.max_in = std::max(t.max_in, segs[b].in_len);
+      t.out_rows += segs[b].out_len; t.in_rows += segs[b].in_len;
+    }
+    t.segs = push(segs); t.tiles = push(tiles);
+    t.nseg = (int)segs.size(); t.ntiles = (int)tiles.size();
+    return t;
+  }
   int tables_upload() {
     if (stage.size() > tables_cap) { set_error("internal: table staging overflow"); return TTSB_E_INVALID; }
     if (stage.size() > e.pinned_cap) {
@@ -429,6 +460,24 @@ struct Run {
     double* p = stats_base + stats_off;
     stats_off += n;
     return p;
+  }
+  // tap of a buffer whose utterances are not contiguous (row offsets / lengths given per utterance)
+  int tap_ragged(const char* name, const float* d, int64_t cols, int64_t ld, const std::vector<int>& offs, const std::vector<int>& lens) {
+    if (!e.taps_on) return TTSB_OK;
+    int64_t rows = 0;
+    for (int l : lens) rows += l;
+    Tap& t = e.taps[name];
+    if (t.d) cudaFree(t.d);
+    t.d = nullptr; t.rows = rows; t.cols = cols;
+    if (rows * cols == 0) return TTSB_OK;
+    CK(cudaMalloc(&t.d, sizeof(float) * rows * cols));
+    int64_t o = 0;
+    for (size_t b = 0; b < lens.size(); ++b) {
+      CK(cudaMemcpy2DAsync(t.d + o * cols, cols * sizeof(float), d + (int64_t)offs[b] * ld, ld * sizeof(float), cols * sizeof(float), lens[b],
+                           cudaMemcpyDeviceToDevice, s));
+      o += lens[b];
+    }
+    return TTSB_OK;
   }
   int tap(const char* name, const float* d, int64_t rows, int64_t cols, int64_t ld) {
     if (!e.taps_on) return TTSB_OK;
@@ -593,11 +642,25 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   }
   Space spU0, spS0, spU1, spS1, spA;
   spU0.build(lU0); spS0.build(lS0); spU1.build(lU1); spS1.build(lS1); spA.build(lA);
-  RC(r.tables_begin((size_t)nseg * 16 * sizeof(Seg) + (size_t)(spS1.total / 128 + 8 * nseg + 64) * 4 * sizeof(Tile) + 4096));
-  const SegTab tL_S1 = r.make_tab(spL, spS1, 1, 1, false);   // source + STFT
+  RC(r.tables_begin((size_t)nseg * 20 * sizeof(Seg) + (size_t)(spS1.total / 128 + 8 * nseg + 64) * 5 * sizeof(Tile) + 4096));
+  // STFT-frame rows of the source features: every utterance starts at a multiple of 6 rows and is zero-padded to 60L+6 rows,
+  // so that six consecutive frames can be viewed as one 144-float row (noise_convs[0] without a strided kernel)
+  std::vector<int> offH(nseg), lenH(nseg);
+  std::vector<Seg> sgL_H(nseg), sgH_S1(nseg), sgHb_S0(nseg);
+  int totH = 0;
+  for (int b = 0; b < nseg; ++b) {
+    const int L = spL.len[b];
+    offH[b] = totH; lenH[b] = 60 * L + 1;
+    sgL_H[b] = {spL.off[b], L, totH, 60 * L + 1};
+    sgH_S1[b] = {totH, 60 * L + 1, spS1.off[b], 60 * L + 1};
+    sgHb_S0[b] = {totH / 6, 10 * L + 1, spS0.off[b], 10 * L};
+    totH += 60 * L + 6;
+  }
+  const SegTab tL_S1 = r.make_tab_segs(sgL_H, false);        // source + STFT
+  const SegTab tH_S1 = r.make_tab_segs(sgH_S1);              // noise_convs[1] (k1)
+  const SegTab tHb_S0 = r.make_tab_segs(sgHb_S0);            // noise_convs[0] over 6-frame blocks
   const SegTab tL_U0 = r.make_tab(spL, spU0);          // ups[0] polyphase
   const SegTab tU0_S0 = r.make_tab(spU0, spS0, 10, 1, false); // flat polyphase rows -> stage-0 rows
-  const SegTab tS1_S0 = r.make_tab(spS1, spS0);        // noise_convs[0] (stride 6)
   const SegTab tS0 = r.make_tab(spS0, spS0);
   const SegTab tS0_U1 = r.make_tab(spS0, spU1);        // ups[1] polyphase
   const SegTab tU1_S1 = r.make_tab(spU1, spS1, 6, 1, false);
@@ -607,12 +670,13 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
 
   // ---- harmonic source + STFT (W10, W11) ----
   float* phase = r.alloc<float>((size_t)spL.total * 9);
-  float* har = r.alloc<float>((size_t)spS1.total * 24);
+  float* har = r.alloc<float>((size_t)totH * 24);
+  if (har) CK(cudaMemsetAsync(har, 0, sizeof(float) * (size_t)totH * 24, r.s));
   float* har_src = e.taps_on ? r.alloc<float>((size_t)spA.total) : nullptr;
   if (!phase || !har) return TTSB_E_NOMEM;
   CK(launch_source_stft(f0, noise, e.src_lin_w, e.src_lin_b, har_src, har, 24, phase, tL_S1.segs, nseg, spL.maxlen, seed, r.s));
   if (har_src) RC(r.tap("har_source", har_src, spA.total, 1, 1));
-  RC(r.tap("har", har, spS1.total, 22, 24));
+  RC(r.tap_ragged("har", har, 22, 24, offH, lenH));
 
   const float* xin = gen_in;      // stage input, ld = Cin of ups[i]
   float* stage_out = nullptr;
@@ -629,8 +693,9 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
     float* xs2 = r.alloc<float>(n);
     double* st_xs = r.stats(nseg, C);
     if (!xs || !xt || !xs2 || !st_xs) return TTSB_E_NOMEM;
-    ConvCall cn; cn.w = &e.noise_conv[i]; cn.x = har; cn.ldx = 24; cn.y = xs; cn.ldy = C; cn.ostats = st_xs; cn.tensor = false;
-    if (i == 0) { cn.stride = 6; cn.pad = 3; RC(run_conv(r, cn, tS1_S0)); } else { RC(run_conv(r, cn, tS1)); }
+    ConvCall cn; cn.x = har; cn.y = xs; cn.ldy = C; cn.ostats = st_xs; cn.tensor = true;
+    if (i == 0) { cn.w = &e.noise_conv0r; cn.ldx = 144; cn.pad = 1; RC(run_conv(r, cn, tHb_S0)); }
+    else { cn.w = &e.noise_conv[1]; cn.ldx = 24; RC(run_conv(r, cn, tH_S1)); }
     RC(run_resblock1(r, e.noise_res[i], xs, st_xs, xs, xt, xs2, 1.0f, 0, nullptr, gbD, ld_gb, tS));
     // x = ups[i](leaky_relu(x, 0.1))  (+ ReflectionPad1d((1,0)) for the last stage) + x_source
     float* up = r.alloc<float>((size_t)spU.total * s_up * C);

@@ -140,6 +140,7 @@ struct Engine {
   float *f0conv_w = nullptr, *f0conv_b = nullptr, *nconv_w = nullptr, *nconv_b = nullptr;
   float *src_lin_w = nullptr, *src_lin_b = nullptr;
   ConvW noise_conv[2], ups[2], conv_post;
+  ConvW noise_conv0r;                           // noise_convs[0] (k12, stride 6) as a k3 conv over rows regrouped 6 at a time
   ResBlock1W noise_res[2], resblk[6];
 
   // ---- state between begin() and finish() ----

@@ -117,72 +117,112 @@ __global__ void fill_style_kernel(const float* __restrict__ style, int ld_style,
 // ALBERT self-attention: qkv rows [.., 3*H*64] (q | k | v), one warp per (query row, head).
 // scores/softmax exactly two-pass (max, exp, sum) like torch.softmax; 1/sqrt(64) applied to the scores.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int ATT_MAXK = 16;  // keys per lane: T <= 512
+constexpr int ATT_MAXK = 16;   // keys per lane: T <= 512
+constexpr int ATT_QW = 16;     // queries (warps) per CTA
+constexpr int ATT_KC = 128;    // keys per shared-memory chunk
+constexpr int ATT_LD = 68;     // padded row (floats): 16-B aligned, conflict-free for LDS.128 across rows
 
-__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, const Seg* __restrict__ segs, int heads) {
+// One CTA = 16 queries of one (utterance, head).  K and V are staged through shared memory in chunks of 128 keys
+// (coalesced loads, every key row is read once per CTA instead of once per warp); lane = key for the scores,
+// lane = output dimension pair for P V.  Two-pass softmax (max, exp, sum) as torch.softmax.
+__global__ void __launch_bounds__(ATT_QW * 32) attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, const Seg* __restrict__ segs, int heads) {
+  __shared__ __align__(16) float kv[ATT_KC][ATT_LD];
   const Seg seg = segs[blockIdx.z];
   const int head = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qi = blockIdx.x * 8 + warp;
-  if (qi >= seg.in_len) return;
+  const int q0 = blockIdx.x * ATT_QW;
+  if (q0 >= seg.in_len) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qi = q0 + warp;
+  const bool valid = qi < seg.in_len;
   const int H = heads * 64;
   const int ld = 3 * H;
-  const float* qrow = qkv + (size_t)(seg.in_off + qi) * ld + head * 64;
+  const int len = seg.in_len;
+  const int nchunk = (len + ATT_KC - 1) / ATT_KC;
   float q[64];
+  if (valid) {
+    const float* qrow = qkv + (size_t)(seg.in_off + qi) * ld + head * 64;
 #pragma unroll
-  for (int d = 0; d < 64; d += 4) {
-    const float4 t = *reinterpret_cast<const float4*>(qrow + d);
-    q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
+    for (int d = 0; d < 64; d += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(qrow + d);
+      q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
+    }
   }
+  auto stage = [&](int chunk, int col_off) {       // rows [chunk*128, +128) of K (col_off = H) or V (2H) -> shared memory
+#pragma unroll
+    for (int it = 0; it < (ATT_KC * 16) / (ATT_QW * 32); ++it) {
+      const int idx = tid + it * (ATT_QW * 32);
+      const int r = idx >> 4, c4 = idx & 15;
+      const int key = chunk * ATT_KC + r;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (key < len) t = *reinterpret_cast<const float4*>(qkv + (size_t)(seg.in_off + key) * ld + col_off + head * 64 + c4 * 4);
+      *reinterpret_cast<float4*>(&kv[r][c4 * 4]) = t;
+    }
+  };
   float sc[ATT_MAXK];
+#pragma unroll
+  for (int i = 0; i < ATT_MAXK; ++i) sc[i] = -INFINITY;
   float mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < ATT_MAXK; ++i) {
-    const int kj = lane + i * 32;
-    float s = -INFINITY;
-    if (kj < seg.in_len) {
-      const float* krow = qkv + (size_t)(seg.in_off + kj) * ld + H + head * 64;
-      float a = 0.f;
+  for (int chunk = 0; chunk < ATT_MAXK / 4; ++chunk) {
+    if (chunk < nchunk) {
+      __syncthreads();
+      stage(chunk, H);
+      __syncthreads();
+      if (valid) {
 #pragma unroll
-      for (int d = 0; d < 64; d += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(krow + d);
-        a = fmaf(q[d], t.x, a); a = fmaf(q[d + 1], t.y, a); a = fmaf(q[d + 2], t.z, a); a = fmaf(q[d + 3], t.w, a);
+        for (int j = 0; j < 4; ++j) {
+          const int kl = j * 32 + lane;
+          if (chunk * ATT_KC + kl < len) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < 64; d += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(&kv[kl][d]);
+              a = fmaf(q[d], t.x, a); a = fmaf(q[d + 1], t.y, a); a = fmaf(q[d + 2], t.z, a); a = fmaf(q[d + 3], t.w, a);
+            }
+            sc[chunk * 4 + j] = a * 0.125f;
+            mx = fmaxf(mx, sc[chunk * 4 + j]);
+          }
+        }
       }
-      s = a * 0.125f;
     }
-    sc[i] = s;
-    mx = fmaxf(mx, s);
   }
   mx = warp_max(mx);
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < ATT_MAXK; ++i) {
-    const int kj = lane + i * 32;
-    const float e = (kj < seg.in_len) ? expf(sc[i] - mx) : 0.f;
+    const float e = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - mx);
     sc[i] = e;
     sum += e;
   }
   sum = warp_sum(sum);
-  const float inv = 1.0f / sum;
-  // out[d] = sum_k p[k] v[k][d]; lane owns dims lane and lane+32
+  const float inv = valid ? 1.0f / sum : 0.f;
   float o0 = 0.f, o1 = 0.f;
-  const int nk = seg.in_len;
 #pragma unroll
-  for (int i = 0; i < ATT_MAXK; ++i) {
-    const int base = i * 32;
-    if (base >= nk) break;
-    const float pi = sc[i] * inv;
-    const int lim = min(32, nk - base);
-    for (int l = 0; l < lim; ++l) {
-      const float pk = __shfl_sync(0xffffffffu, pi, l);
-      const float* vrow = qkv + (size_t)(seg.in_off + base + l) * ld + 2 * H + head * 64;
-      o0 = fmaf(pk, vrow[lane], o0);
-      o1 = fmaf(pk, vrow[lane + 32], o1);
+  for (int chunk = 0; chunk < ATT_MAXK / 4; ++chunk) {
+    if (chunk < nchunk) {
+      __syncthreads();
+      stage(chunk, 2 * H);
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int base = chunk * ATT_KC + j * 32;
+        if (base < len) {
+          const float pi = sc[chunk * 4 + j] * inv;
+          const int lim = min(32, len - base);
+          for (int l = 0; l < lim; ++l) {
+            const float pk = __shfl_sync(0xffffffffu, pi, l);
+            o0 = fmaf(pk, kv[j * 32 + l][lane], o0);
+            o1 = fmaf(pk, kv[j * 32 + l][lane + 32], o1);
+          }
+        }
+      }
     }
   }
-  float* orow = ctx + (size_t)(seg.in_off + qi) * H + head * 64;
-  orow[lane] = o0;
-  orow[lane + 32] = o1;
+  if (valid) {
+    float* orow = ctx + (size_t)(seg.in_off + qi) * H + head * 64;
+    orow[lane] = o0;
+    orow[lane + 32] = o1;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -336,8 +376,8 @@ cudaError_t launch_fill_style(const float* style, int ld_style, int style_off, c
 cudaError_t launch_attention(const float* qkv, float* ctx, const Seg* segs, int nseg, int max_len, int heads, cudaStream_t s) {
   if (nseg <= 0 || max_len <= 0) return cudaSuccess;
   if (max_len > 32 * ATT_MAXK) return cudaErrorInvalidValue;
-  dim3 grid((max_len + 7) / 8, heads, nseg);
-  attention_kernel<<<grid, 256, 0, s>>>(qkv, ctx, segs, heads);
+  dim3 grid((max_len + ATT_QW - 1) / ATT_QW, heads, nseg);
+  attention_kernel<<<grid, ATT_QW * 32, 0, s>>>(qkv, ctx, segs, heads);
   return launched();
 }
 cudaError_t launch_lstm(const float* gx, const float* whhT, const float* bias, float* y, int ldy, const LstmSeg* segs, int nseg, cudaStream_t s) {
