@@ -136,12 +136,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("TTSB_BENCH_PRECISION", "f16"), choices=["f16", "bf16", "fp32"])
-    ap.add_argument("--ref-utts", type=int, default=2, help="utterances per step of the CPU reference arm")
-    ap.add_argument("--cpu-baseline-utts", type=int, default=2)
+    ap.add_argument("--ref-utts", type=int, default=8, help="utterances per step of the CPU reference arm")
+    ap.add_argument("--cpu-baseline-utts", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
