@@ -32,7 +32,7 @@ constexpr int NPW = 8;                  // producer / epilogue warps
 constexpr int NPROD = NPW * 32;
 constexpr int NEPI = 128;               // 4 epilogue warps (one per TMEM lane quadrant)
 constexpr int NTHREADS = NPROD + 64 + NEPI;   // producers (0-7), weight loader (8), MMA issuer (9), epilogue (10-13)
-constexpr int MAXSTAGE = 4;
+constexpr int MAXSTAGE = 8;
 // split-fp16 mode: operands are pre-scaled by powers of two so that the low halves stay in fp16's normal range
 constexpr float SPLIT_SA = 16.f, SPLIT_SW = 256.f;
 constexpr int STG_LD = 36;              // floats per staging row (32 + 4 pad: 16-B aligned rows, conflict-free both ways)
@@ -388,7 +388,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     }
   } else if (warp == NPW + 1) {
     // =================== MMA issuer ===================
-    if (lane == 0) {
+    // The whole warp walks the loops with warp-uniform values (descriptors then live in uniform registers) and one elected
+    // lane issues tcgen05.mma / tcgen05.commit.  Issuing from inside `if (lane == 0)` made the compiler shuttle every operand
+    // through R2UR and wrap each UTCHMMA in an ELECT loop: ~190 cycles per MMA against 64-128 cycles of tensor-core time.
+    {
+      uint32_t leader;
+      asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(leader));
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t ofmt = WFMT >= 1 ? 0u : 1u;       // instruction-descriptor operand format: 0 = F16, 1 = BF16
       const uint32_t a_lo = (uint32_t)(pl.KS >> 3) * (uint32_t)pl.SR * 16u;     // split mode: offset of the low-half planes
       const uint32_t b_lo = (uint32_t)pl.BN * KCH * 2u;                         //             and of the low-half weight block
@@ -405,7 +411,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         const uint32_t slot = n & 1u;
         mbar_wait_t(bar_acc_empty(slot), ((n >> 1) & 1u) ^ 1u, tw_acc);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tacc = tmem_base + slot * (uint32_t)pl.acc_cols;
+        const uint32_t tacc = tmem_u + slot * (uint32_t)pl.acc_cols;
         const uint32_t tcor = tacc + (uint32_t)pl.BN;       // split mode: the small cross terms get their own accumulator
         uint32_t first = 1;
         for (int sc = 0; sc < pl.nsc; ++sc, ++g) {
@@ -428,23 +434,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
               for (int kk = 0; kk < KCH / 16; ++kk) {
                 const uint64_t ad = ad0 + (uint64_t)(kk * a_kstep);
                 const uint64_t bd = bd0 + (uint64_t)(kk * b_kstep);
-                if (!(u.dbg & 4)) umma_bf16(tacc, ad, bd, idesc, first ? 0u : 1u);
+                if (leader && !(u.dbg & 4)) umma_bf16(tacc, ad, bd, idesc, first ? 0u : 1u);
                 if (WFMT == 2) {
                   // x w ~= xh wh + (xh wl + xl wh)   (xl wl is ~2^-22 relative and dropped).  The tensor core truncates at
                   // every accumulate, an error that grows linearly with the number of MMAs into one accumulator: the cross
                   // terms (2^-11 of the main term) go to their own accumulator, so the main one sees K/16 steps, not 3K/16
-                  umma_bf16(tcor, ad, bd + (uint64_t)(b_lo >> 4), idesc, first ? 0u : 1u);
-                  umma_bf16(tcor, ad + (uint64_t)(a_lo >> 4), bd, idesc, 1u);
+                  if (leader) {
+                    umma_bf16(tcor, ad, bd + (uint64_t)(b_lo >> 4), idesc, first ? 0u : 1u);
+                    umma_bf16(tcor, ad + (uint64_t)(a_lo >> 4), bd, idesc, 1u);
+                  }
                 }
                 first = 0;
               }
-              umma_commit(bar_empty(s));            // weight stage free once these MMAs have read it
+              if (leader) umma_commit(bar_empty(s));            // weight stage free once these MMAs have read it
+              __syncwarp();
             }
-          umma_commit(bar_slab_empty(b));           // slab free once every MMA issued so far has completed
+          if (leader) umma_commit(bar_slab_empty(b));           // slab free once every MMA issued so far has completed
         }
-        umma_commit(bar_acc_full(slot));            // accumulator of this item complete
+        if (leader) umma_commit(bar_acc_full(slot));            // accumulator of this item complete
       }
-      if (u.prof) {
+      if (u.prof && lane == 0) {
         long long* pp = u.prof + blockIdx.x * 16;
         pp[2] = clock64() - t_start; pp[3] = tw_slab; pp[4] = tw_acc; pp[5] = tw_w;
       }
