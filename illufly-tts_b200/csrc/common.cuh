@@ -95,7 +95,7 @@ cudaError_t launch_dur_scan(const int* pred_dur, const Seg* segs, int nseg, int*
 cudaError_t launch_indices(const int* cum, const Seg* segs, int nseg, int* indices, int total_frames, const int* frame2seg, cudaStream_t s);
 cudaError_t launch_gather_rows(const float* src, int lds, const int* indices, const int* frame2seg, const Seg* segs, float* dst, int ldd,
                                int C, int rows, cudaStream_t s);
-cudaError_t launch_colstats(const float* x, int ldx, int C, const Seg* segs, int nseg, double* stats, int ld_stats, cudaStream_t s);
+cudaError_t launch_colstats(const float* x, int ldx, int C, const Seg* segs, int nseg, int max_len, double* stats, int ld_stats, cudaStream_t s);
 cudaError_t launch_pool_up2(const float* x, int ldx, float* y, int ldy, int C, const float* w, const float* bias,
                             const double* pstats, int ld_pstats, const float* gb, int ld_gb, int beta_off, float slope,
                             const Seg* segs, int nseg, int max_out_len, cudaStream_t s);

@@ -964,7 +964,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   float* NN = r.alloc<float>(RL);
   if (!GX || !SH || !st_sh || !F0 || !NN) return TTSB_E_NOMEM;
   RC(run_bilstm(r, e.shared_lstm, EN, 640, GX, SH, 512, tF, d_lsF, (int)g_lsF.size(), false));
-  CK(launch_colstats(SH, 512, 512, tF.segs, B, st_sh, 512, r.s));
+  CK(launch_colstats(SH, 512, 512, tF.segs, B, spF.maxlen, st_sh, 512, r.s));
   for (int br = 0; br < 2; ++br) {
     const ResBlk1dW* blk = br == 0 ? e.f0_blk : e.n_blk;
     float* o0 = r.alloc<float>((size_t)RF * 512);
@@ -993,7 +993,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   double* st_a = r.stats(B, 1090); double* st_b = r.stats(B, 1090);
   float* GIN = r.alloc<float>((size_t)RL * 512);
   if (!st_cat0 || !XDa || !XDb || !st_a || !st_b || !GIN) return TTSB_E_NOMEM;
-  CK(launch_colstats(CAT0, 516, 514, tF.segs, B, st_cat0, 514, r.s));
+  CK(launch_colstats(CAT0, 516, 514, tF.segs, B, spF.maxlen, st_cat0, 514, r.s));
   CK(cudaMemsetAsync(XDa, 0, sizeof(float) * (size_t)RF * 1092, r.s));
   CK(cudaMemsetAsync(XDb, 0, sizeof(float) * (size_t)RF * 1092, r.s));
   // tail columns [asr_res(64) | F0 | N] are the same for every decode block: write them into both ping-pong buffers
@@ -1003,8 +1003,8 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
     CK(launch_copy_cols(CAT0 + 512, 516, xd + 1088, 1092, 2, RF, r.s));
   }
   // statistics rows are [B][1090][2]: per-utterance tail statistics via one strided column-statistics pass per buffer
-  CK(launch_colstats(XDa + 1024, 1092, 66, tF.segs, B, st_a + 1024 * 2, 1090, r.s));
-  CK(launch_colstats(XDb + 1024, 1092, 66, tF.segs, B, st_b + 1024 * 2, 1090, r.s));
+  CK(launch_colstats(XDa + 1024, 1092, 66, tF.segs, B, spF.maxlen, st_a + 1024 * 2, 1090, r.s));
+  CK(launch_colstats(XDb + 1024, 1092, 66, tF.segs, B, spF.maxlen, st_b + 1024 * 2, 1090, r.s));
   // the conv epilogue accumulates [B][Cout=1024][2]; the AdaIN prologue of the next block reads [B][1090][2]: give the
   // producer a dense scratch and scatter it (tiny copies) — done by colstats-free strided memcpy below
   double* st_tmp = r.stats(B, 1024);

@@ -219,7 +219,7 @@ int ttsb_engine_read_tap(ttsb_engine* h, const char* name, float* out, int64_t* 
 // single-kernel entry points
 // ---------------------------------------------------------------------------------------------------------
 int ttsb_op_istft(ttsb_engine* h, const float* cp, int ld, const int32_t* frame_counts_F, int B, float* audio, float* ms) {
-  if (!h || !cp || !frame_counts_F || B <= 0 || !audio || ld < 22) { set_error("op_istft: bad arguments"); return TTSB_E_INVALID; }
+  if (!h || !cp || !frame_counts_F || B <= 0 || !audio || ld < 24 || (ld & 3)) { set_error("op_istft: bad arguments (rows must hold >= 24 floats, 16-byte aligned)"); return TTSB_E_INVALID; }
   Engine& e = h->e;
   CKA(cudaSetDevice(e.device));
   e.begun = false; e.arena.reset();
@@ -253,7 +253,7 @@ int ttsb_op_adain_snake(ttsb_engine* h, const float* x, float* y, int C, const i
   {
     OpTimer tm(e, ms_stats);
     CKA(tm.start());
-    CKA(launch_colstats(x, C, C, t.segs, B, st, C, e.stream));
+    CKA(launch_colstats(x, C, C, t.segs, B, t.maxlen, st, C, e.stream));
     CKA(tm.stop());
   }
   {

@@ -34,34 +34,41 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------------------
 // per-(utterance, channel) sum and sum of squares over time (double), for InstanceNorm
-// grid (ceil(C/32), splits, nseg), block (32, 8)
+// grid (ceil(C/128), row splits, nseg), block (32, 8): a thread owns 4 channels (one 16-B load per row when aligned)
 // ---------------------------------------------------------------------------------------------------------
+constexpr int CS_ROWS = 512;    // rows per block
 __global__ void __launch_bounds__(256) colstats_kernel(const float* __restrict__ x, int ldx, int C, const Seg* __restrict__ segs,
                                                        double* __restrict__ stats, int ld_stats) {
-  __shared__ double sh[2][8][32];
+  __shared__ double sh[2][8][128];
   const Seg seg = segs[blockIdx.z];
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c0 = blockIdx.x * 128 + threadIdx.x * 4;
   const int ty = threadIdx.y;
-  const int splits = gridDim.y;
-  const int chunk = (seg.in_len + splits - 1) / splits;
-  const int r0 = blockIdx.y * chunk, r1 = min(seg.in_len, r0 + chunk);
-  double s = 0.0, q = 0.0;
-  if (c < C) {
-    for (int r = r0 + ty; r < r1; r += 8) {
-      const float v = x[(size_t)(seg.in_off + r) * ldx + c];
-      s += (double)v;
-      q += (double)v * (double)v;
-    }
-  }
-  sh[0][ty][threadIdx.x] = s;
-  sh[1][ty][threadIdx.x] = q;
-  __syncthreads();
-  if (ty == 0 && c < C && r0 < r1) {
+  const int r0 = blockIdx.y * CS_ROWS, r1 = min(seg.in_len, r0 + CS_ROWS);
+  if (r0 >= seg.in_len) return;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool vec = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && c0 + 3 < C;
+  for (int r = r0 + ty; r < r1; r += 8) {
+    const float* row = x + (size_t)(seg.in_off + r) * ldx + c0;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) { const float4 t = *reinterpret_cast<const float4*>(row); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else {
 #pragma unroll
-    for (int i = 1; i < 8; ++i) { s += sh[0][i][threadIdx.x]; q += sh[1][i][threadIdx.x]; }
-    double* st = stats + ((size_t)blockIdx.z * ld_stats + c) * 2;
-    atomicAdd(st, s);
-    atomicAdd(st + 1, q);
+      for (int e = 0; e < 4; ++e) if (c0 + e < C) v[e] = row[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { s[e] += v[e]; q[e] = fmaf(v[e], v[e], q[e]); }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { sh[0][ty][threadIdx.x * 4 + e] = (double)s[e]; sh[1][ty][threadIdx.x * 4 + e] = (double)q[e]; }
+  __syncthreads();
+  const int t = ty * 32 + threadIdx.x;          // 256 threads: first 128 reduce the sums, the other 128 the squares
+  const int which = t >> 7, cl = t & 127;
+  const int c = blockIdx.x * 128 + cl;
+  if (c < C) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a += sh[which][i][cl];
+    atomicAdd(stats + ((size_t)blockIdx.z * ld_stats + c) * 2 + which, a);
   }
 }
 
@@ -72,36 +79,37 @@ __global__ void zero_f64_kernel(double* p, size_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+constexpr int AS_ROWS = 256;    // rows per block
 // standalone AdaIN1d + Snake pass (A.8 + A.12): y = v + (1/alpha) sin^2(alpha v), v = (1+g)(x-mean)rstd + b
 // 8 B/element algorithmic (statistics come from the producer's epilogue).  grid (row tiles of 32, nseg)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adain_snake_kernel(const float* __restrict__ x, int ldx, float* __restrict__ y, int ldy, int C,
                                                           const double* __restrict__ pstats, int ld_pstats, const float* __restrict__ gb, int ld_gb,
                                                           int beta_off, const float* __restrict__ alpha, const Seg* __restrict__ segs) {
-  extern __shared__ float coef[];   // [4][C] mean, a, b, alpha
+  extern __shared__ float coef[];   // [5][C]: A, B + k, 2 alpha A, 2 alpha B, k   (same folding as the conv kernel's producer)
   const Seg seg = segs[blockIdx.y];
-  const int r0 = blockIdx.x * 32;
+  const int r0 = blockIdx.x * AS_ROWS;
   if (r0 >= seg.in_len) return;
-  float* s_mean = coef; float* s_a = coef + C; float* s_b = coef + 2 * C; float* s_al = coef + 3 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, a, b;
     adain_coef(pstats + ((size_t)blockIdx.y * ld_pstats + c) * 2, seg.in_len, gb[(size_t)blockIdx.y * ld_gb + c],
                gb[(size_t)blockIdx.y * ld_gb + beta_off + c], mean, a, b);
-    s_mean[c] = mean; s_a[c] = a; s_b[c] = b; s_al[c] = alpha[c];
+    const float al = alpha[c];
+    const float Bf = fmaf(-mean, a, b), k = 0.5f / al;
+    coef[c] = a; coef[C + c] = Bf + k; coef[2 * C + c] = 2.f * al * a; coef[3 * C + c] = 2.f * al * Bf; coef[4 * C + c] = k;
   }
   __syncthreads();
   const int C4 = C >> 2;
-  const int r1 = min(seg.in_len, r0 + 32);
+  const int r1 = min(seg.in_len, r0 + AS_ROWS);
   for (int idx = threadIdx.x; idx < (r1 - r0) * C4; idx += blockDim.x) {
     const int r = r0 + idx / C4, c = (idx % C4) * 4;
     const float4 v = *reinterpret_cast<const float4*>(x + (size_t)(seg.in_off + r) * ldx + c);
-    float4 o;
-    float al;
-    al = s_al[c];     o.x = snake(fmaf(v.x - s_mean[c], s_a[c], s_b[c]), al, 1.0f / al);
-    al = s_al[c + 1]; o.y = snake(fmaf(v.y - s_mean[c + 1], s_a[c + 1], s_b[c + 1]), al, 1.0f / al);
-    al = s_al[c + 2]; o.z = snake(fmaf(v.z - s_mean[c + 2], s_a[c + 2], s_b[c + 2]), al, 1.0f / al);
-    al = s_al[c + 3]; o.w = snake(fmaf(v.w - s_mean[c + 3], s_a[c + 3], s_b[c + 3]), al, 1.0f / al);
-    *reinterpret_cast<float4*>(y + (size_t)(seg.out_off + r) * ldy + c) = o;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      o[e] = fmaf(-coef[4 * C + c + e], __cosf(fmaf(vv[e], coef[2 * C + c + e], coef[3 * C + c + e])), fmaf(vv[e], coef[c + e], coef[C + c + e]));
+    *reinterpret_cast<float4*>(y + (size_t)(seg.out_off + r) * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -300,62 +308,97 @@ __global__ void __launch_bounds__(128) up_add_kernel(const float* __restrict__ u
 
 // ---------------------------------------------------------------------------------------------------------
 // conv_post epilogue + iSTFT (A.11): spec = exp(x[:11]), phase = sin(x[11:]), z = spec e^{j phase};
-// y = overlap-add(irfft20(z) * hann) / sum(hann^2), centre-trimmed.   One CTA = 320 output samples of one utterance.
-// Algorithmic bytes: read 22 fp32 per frame, write 5 fp32 per frame  (12.96 kB per decoder frame F).
+// y = overlap-add(irfft20(z) * hann) / sum(hann^2), centre-trimmed.
+// One thread = one STFT frame: its 22 inputs come in with six 16-B loads, the 20 windowed irfft outputs are produced in
+// registers with compile-time twiddles (the even / odd symmetry of cos / sin halves the work) and parked in shared memory;
+// then the block writes 5 output samples per frame, each the sum of the 4 frames that overlap it, coalesced.
+// Algorithmic bytes: read 22 fp32 per frame, write 5 fp32 per frame  (12.96 kB per decoder frame F): HBM bound.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int IS_SAMP = 320;
-constexpr int IS_FR = IS_SAMP / 5 + 4;   // frames touching the tile
-__global__ void __launch_bounds__(IS_SAMP) istft_kernel(const float* __restrict__ cp, int ld, float* __restrict__ audio, const Seg* __restrict__ segs) {
-  __shared__ float re[IS_FR][12], im[IS_FR][12];
+constexpr int IS_FPB = 256;                 // frames (= 1280 output samples) per block
+constexpr int IS_HALO = 3;                  // a sample also needs the 3 frames before its own
+constexpr int IS_LD = 21;                   // padded frame row in shared memory
+
+struct Tw20 {                               // cos / sin(2 pi i / 20) as compile-time constants
+  __host__ __device__ static constexpr float c(int i) {
+    constexpr float t[20] = {1.0f, 0.951056516295153572f, 0.809016994374947424f, 0.587785252292473129f, 0.309016994374947424f, 0.0f,
+                             -0.309016994374947424f, -0.587785252292473129f, -0.809016994374947424f, -0.951056516295153572f, -1.0f,
+                             -0.951056516295153572f, -0.809016994374947424f, -0.587785252292473129f, -0.309016994374947424f, 0.0f,
+                             0.309016994374947424f, 0.587785252292473129f, 0.809016994374947424f, 0.951056516295153572f};
+    return t[i % 20];
+  }
+  __host__ __device__ static constexpr float s(int i) { return c((i + 15) % 20); }   // sin(x) = cos(x - pi/2)
+  __host__ __device__ static constexpr float w(int m) { return 0.5f * (1.0f - c(m)); }   // periodic Hann(20)
+};
+
+__global__ void __launch_bounds__(IS_FPB + 32) istft_kernel(const float* __restrict__ cp, int ld, float* __restrict__ audio, const Seg* __restrict__ segs) {
+  __shared__ float fr_out[(IS_FPB + IS_HALO) * IS_LD];
   const Seg seg = segs[blockIdx.y];        // in: frames (120F+1), out: samples (600F)
-  const int n0 = blockIdx.x * IS_SAMP;
-  if (n0 >= seg.out_len) return;
-  const int fbase = (n0 + 10 - 19 + 4 + 500) / 5 - 100;   // ceil((n0-9)/5) without negative-division surprises
-  for (int i = threadIdx.x; i < IS_FR * 11; i += blockDim.x) {
-    const int fl = i / 11, k = i % 11;
-    const int fr = fbase + fl;
-    float r = 0.f, q = 0.f;
+  const int f0 = blockIdx.x * IS_FPB;      // this block owns padded-signal samples [5 f0, 5 f0 + 1280)
+  if (5 * f0 - 10 >= seg.out_len) return;
+  const int tid = threadIdx.x;
+  if (tid < IS_FPB + IS_HALO) {
+    const int fr = f0 - IS_HALO + tid;
+    float* o = fr_out + tid * IS_LD;
     if (fr >= 0 && fr < seg.in_len) {
-      const float* row = cp + (size_t)(seg.in_off + fr) * ld;
-      const float mag = expf(row[k]);
-      const float ph = sinf(row[11 + k]);
-      float sn, cs;
-      sincosf(ph, &sn, &cs);
-      r = mag * cs; q = mag * sn;
+      const float4* row = reinterpret_cast<const float4*>(cp + (size_t)(seg.in_off + fr) * ld);
+      float x[24];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { const float4 t = row[i]; x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w; }
+      float re[11], im[11];
+#pragma unroll
+      for (int k = 0; k <= 10; ++k) {
+        const float mag = __expf(x[k]);
+        float sn, cs;
+        __sincosf(__sinf(x[11 + k]), &sn, &cs);
+        re[k] = mag * cs; im[k] = mag * sn;
+      }
+      // x[m] = (X0 + (-1)^m X10 + 2 sum_{k=1..9} (Re_k cos(2 pi k m / 20) - Im_k sin(2 pi k m / 20))) / 20
+      // cos part C[m] is even about m = 10 (C[20-m] = C[m]), sin part S[m] odd: x[m] = C - S, x[20-m] = C + S
+#pragma unroll
+      for (int m = 0; m <= 10; ++m) {
+        float C = re[0] + ((m & 1) ? -re[10] : re[10]);
+        float S = 0.f;
+#pragma unroll
+        for (int k = 1; k <= 9; ++k) {
+          C = fmaf(2.0f * Tw20::c(k * m), re[k], C);
+          S = fmaf(2.0f * Tw20::s(k * m), im[k], S);
+        }
+        o[m] = (C - S) * (0.05f * Tw20::w(m));
+        if (m >= 1 && m <= 9) o[20 - m] = (C + S) * (0.05f * Tw20::w(20 - m));
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < 20; ++m) o[m] = 0.f;
     }
-    re[fl][k] = r; im[fl][k] = q;
   }
   __syncthreads();
-  const int n = n0 + threadIdx.x;
-  if (n >= seg.out_len) return;
-  const int p = n + 10;
-  float acc = 0.f, env = 0.f;
-  const int fhi = p / 5;
+  // 1280 samples of the padded signal, index p; output sample n = p - 10
+  for (int i = tid; i < 5 * IS_FPB; i += blockDim.x) {
+    const int p = 5 * f0 + i;
+    const int n = p - 10;
+    if (n < 0 || n >= seg.out_len) continue;
+    const int fl = i / 5 + IS_HALO;          // local index of frame floor(p / 5)
+    const int r = i - 5 * (i / 5);
+    float acc = 0.f, env = 0.f;
 #pragma unroll
-  for (int d = 0; d < 4; ++d) {
-    const int fr = fhi - d;
-    const int m = p - 5 * fr;            // 0..19
-    if (fr < 0 || fr >= seg.in_len || m > 19) continue;
-    const int fl = fr - fbase;
-    float v = re[fl][0] + ((m & 1) ? -re[fl][10] : re[fl][10]);
-#pragma unroll
-    for (int k = 1; k <= 9; ++k) {
-      const int tw = (k * m) % 20;
-      v = fmaf(2.0f * re[fl][k], c_cos20[tw], v);
-      v = fmaf(-2.0f * im[fl][k], c_sin20[tw], v);
+    for (int d = 0; d < 4; ++d) {
+      const int fr = f0 + i / 5 - d;
+      if (fr >= 0 && fr < seg.in_len) {
+        const int m = r + 5 * d;
+        acc += fr_out[(fl - d) * IS_LD + m];
+        const float w = 0.5f * (1.0f - c_cos20[m]);
+        env = fmaf(w, w, env);
+      }
     }
-    const float w = c_hann20[m];
-    acc = fmaf(v * 0.05f, w, acc);
-    env = fmaf(w, w, env);
+    audio[(size_t)seg.out_off + n] = acc / env;
   }
-  audio[(size_t)seg.out_off + n] = acc / env;
 }
 
 }  // namespace
 
-cudaError_t launch_colstats(const float* x, int ldx, int C, const Seg* segs, int nseg, double* stats, int ld_stats, cudaStream_t s) {
-  if (nseg <= 0 || C <= 0) return cudaSuccess;
-  dim3 grid((C + 31) / 32, 8, nseg), block(32, 8);
+cudaError_t launch_colstats(const float* x, int ldx, int C, const Seg* segs, int nseg, int max_len, double* stats, int ld_stats, cudaStream_t s) {
+  if (nseg <= 0 || C <= 0 || max_len <= 0) return cudaSuccess;
+  dim3 grid((C + 127) / 128, (max_len + CS_ROWS - 1) / CS_ROWS, nseg), block(32, 8);
   colstats_kernel<<<grid, block, 0, s>>>(x, ldx, C, segs, stats, ld_stats);
   return launched();
 }
@@ -368,8 +411,8 @@ cudaError_t launch_adain_snake(const float* x, int ldx, float* y, int ldy, int C
                                int beta_off, const float* alpha, const Seg* segs, int nseg, int max_len, cudaStream_t s) {
   if (nseg <= 0 || max_len <= 0) return cudaSuccess;
   if ((C & 3) || (ldx & 3) || (ldy & 3)) return cudaErrorInvalidValue;
-  dim3 grid((max_len + 31) / 32, nseg);
-  adain_snake_kernel<<<grid, 256, 4 * C * sizeof(float), s>>>(x, ldx, y, ldy, C, pstats, ld_pstats, gb, ld_gb, beta_off, alpha, segs);
+  dim3 grid((max_len + AS_ROWS - 1) / AS_ROWS, nseg);
+  adain_snake_kernel<<<grid, 256, 5 * C * sizeof(float), s>>>(x, ldx, y, ldy, C, pstats, ld_pstats, gb, ld_gb, beta_off, alpha, segs);
   return launched();
 }
 cudaError_t launch_pool_up2(const float* x, int ldx, float* y, int ldy, int C, const float* w, const float* bias,
@@ -418,9 +461,10 @@ cudaError_t launch_istft(const float* cp, int ld, float* audio, const Seg* segs,
   if (nseg <= 0 || max_frames <= 1) return cudaSuccess;
   cudaError_t e = ensure_tables();
   if (e != cudaSuccess) return e;
-  const int max_samples = 5 * (max_frames - 1);
-  dim3 grid((max_samples + IS_SAMP - 1) / IS_SAMP, nseg);
-  istft_kernel<<<grid, IS_SAMP, 0, s>>>(cp, ld, audio, segs);
+  if (ld < 24 || (ld & 3) || (reinterpret_cast<uintptr_t>(cp) & 15)) return cudaErrorInvalidValue;   // rows are read as six float4
+  const int max_samples = 5 * (max_frames - 1) + 10;       // padded-signal samples that matter
+  dim3 grid((max_samples + 5 * IS_FPB - 1) / (5 * IS_FPB), nseg);
+  istft_kernel<<<grid, IS_FPB + 32, 0, s>>>(cp, ld, audio, segs);
   return launched();
 }
 

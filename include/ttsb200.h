@@ -142,7 +142,7 @@ TTSB_API int ttsb_engine_read_tap(ttsb_engine* e, const char* name, float* out, 
  * each returns the CUDA-event time of the launch(es) in *ms when ms != NULL (the call then synchronises). */
 
 /* fused conv_post epilogue + iSTFT(20,5) overlap-add (kokoro TorchSTFT.inverse on exp/sin of conv_post):
- *   cp dev fp32 [sum frames, ld] (cols 0..10 log-magnitude, 11..21 phase argument), frames_b = 120 F_b + 1,
+ *   cp dev fp32 [sum frames, ld >= 24, ld % 4 == 0] (cols 0..10 log-magnitude, 11..21 phase argument), frames_b = 120 F_b + 1,
  *   audio dev fp32 [600 sum F]                                                                                  */
 TTSB_API int ttsb_op_istft(ttsb_engine* e, const float* cp, int ld, const int32_t* frame_counts_F, int B, float* audio, float* ms);
 /* AdaIN1d + Snake over channels-last rows: y = v + sin^2(alpha v)/alpha, v = (1+g)(x-mean)rstd + b; statistics
