@@ -53,7 +53,7 @@ struct ConvArgs {
   const Seg* segs; const Tile* tiles; int ntiles; int tile_rows;
 };
 
-struct LstmSeg {
+struct LstmSeg {                       // host-side description of one utterance's recurrence
   int off, len, pre;                   // rows; `pre` = zero-input steps the REVERSE direction runs first (padded-batch quirk)
 };
 
@@ -74,8 +74,6 @@ cudaError_t launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s);     // tcgen05 bf16 path (k*dil halo, Cin%16==0 after padding)
 bool conv_umma_supported(const ConvArgs& a);
 
-cudaError_t launch_lstm(const float* gx, const float* whhT, const float* bias, float* y, int ldy,
-                        const LstmSeg* segs, int nseg, cudaStream_t s);
 cudaError_t launch_lstm_cluster(const float* gx, const float* whh, const float* bias, float* y, int ldy, const LstmGroup* groups, int ngroups,
                                 cudaStream_t s);
 cudaError_t launch_attention(const float* qkv, float* ctx, const Seg* segs, int nseg, int max_len, int heads, cudaStream_t s);

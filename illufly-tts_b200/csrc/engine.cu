@@ -198,11 +198,6 @@ bool Loader::lstm(const std::string& prefix, LstmW& l) {
     for (int g = 0; g < 1024; ++g) bias[d * 1024 + g] = bih[d]->data[g] + bhh[d]->data[g];
   }
   pack_conv(w, &bias, l.ih, 3);
-  std::vector<float> t((size_t)2 * 256 * 1024);
-  for (int d = 0; d < 2; ++d)
-    for (int g = 0; g < 1024; ++g)
-      for (int kk = 0; kk < 256; ++kk) t[((size_t)d * 256 + kk) * 1024 + g] = whh[d]->data[(size_t)g * 256 + kk];
-  l.whhT = upload(t);
   std::vector<float> o((size_t)2 * 1024 * 256);
   for (int d = 0; d < 2; ++d) memcpy(&o[(size_t)d * 1024 * 256], whh[d]->data.data(), sizeof(float) * 1024 * 256);
   l.whh = upload(o);

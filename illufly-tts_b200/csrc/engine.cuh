@@ -28,7 +28,6 @@ struct ConvW {
 };
 struct LstmW {
   ConvW ih;                               // [In] -> 2048 (fwd i,f,g,o | rev i,f,g,o), bias = b_ih + b_hh
-  float* whhT = nullptr;                  // [2][256][1024] (lstm_kernel)
   float* whh = nullptr;                   // [2][1024][256] (lstm_cluster_kernel: rows contiguous)
 };
 struct AdainRef { int off = 0; int C = 0; };  // slice of the per-utterance gamma|beta row

@@ -368,14 +368,11 @@ int ttsb_op_bilstm(ttsb_engine* h, const float* x, int In, const float* w_ih, co
   OpTables t;
   int rc = t.build(e, l, l);
   if (rc) return rc;
-  std::vector<float> p((size_t)In * 2048), bias(2048), whhT((size_t)2 * 256 * 1024);
+  std::vector<float> p((size_t)In * 2048), bias(2048);
   for (int g = 0; g < 2048; ++g) {
     bias[g] = b_ih[g] + b_hh[g];
     for (int ci = 0; ci < In; ++ci) p[(size_t)ci * 2048 + g] = w_ih[(size_t)g * In + ci];
   }
-  for (int d = 0; d < 2; ++d)
-    for (int g = 0; g < 1024; ++g)
-      for (int kk = 0; kk < 256; ++kk) whhT[((size_t)d * 256 + kk) * 1024 + g] = w_hh[((size_t)d * 1024 + g) * 256 + kk];
   std::vector<LstmGroup> ls((B + LSTM_UB - 1) / LSTM_UB);
   for (auto& g : ls) memset(&g, 0, sizeof(g));
   for (int b = 0, o = 0; b < B; ++b) { ls[b / LSTM_UB].off[b % LSTM_UB] = o; ls[b / LSTM_UB].len[b % LSTM_UB] = l[b]; o += l[b]; }

@@ -226,55 +226,6 @@ __global__ void __launch_bounds__(ATT_QW * 32) attention_kernel(const float* __r
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// BiLSTM recurrence (hidden 256 per direction).  gx = x W_ih^T + b_ih + b_hh for both directions ([rows][2048],
-// gate order i,f,g,o per direction) comes from the GEMM kernel; this kernel runs the serial part:
-// one CTA per (utterance, direction), one thread per gate row, W_hh^T ([dir][256][1024]) streamed from L2
-// with coalesced loads, h broadcast from shared memory.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) lstm_kernel(const float* __restrict__ gx, const float* __restrict__ whhT, const float* __restrict__ bias,
-                                                    float* __restrict__ y, int ldy, const LstmSeg* __restrict__ segs) {
-  __shared__ __align__(16) float h[256];
-  __shared__ float pre[1024];
-  const LstmSeg seg = segs[blockIdx.x];
-  const int dir = blockIdx.y;
-  const int g = threadIdx.x;
-  const float* W = whhT + (size_t)dir * 256 * 1024 + g;
-  const float bg = bias[dir * 1024 + g];
-  float c = 0.f;
-  if (g < 256) h[g] = 0.f;
-  __syncthreads();
-  const int npre = dir ? seg.pre : 0;
-  const int steps = seg.len + npre;
-  for (int s = 0; s < steps; ++s) {
-    const bool is_pad = s < npre;
-    const int t = dir ? (seg.len - 1 - (s - npre)) : s;
-    float a0 = is_pad ? bg : gx[(size_t)(seg.off + t) * 2048 + dir * 1024 + g];
-    float a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < 256; k += 4) {
-      const float4 hv = *reinterpret_cast<const float4*>(&h[k]);
-      a0 = fmaf(W[(size_t)(k + 0) * 1024], hv.x, a0);
-      a1 = fmaf(W[(size_t)(k + 1) * 1024], hv.y, a1);
-      a2 = fmaf(W[(size_t)(k + 2) * 1024], hv.z, a2);
-      a3 = fmaf(W[(size_t)(k + 3) * 1024], hv.w, a3);
-    }
-    pre[g] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (g < 256) {
-      const float ig = sigmoidf_acc(pre[g]);
-      const float fg = sigmoidf_acc(pre[256 + g]);
-      const float gg = tanhf(pre[512 + g]);
-      const float og = sigmoidf_acc(pre[768 + g]);
-      c = fg * c + ig * gg;
-      const float hn = og * tanhf(c);
-      h[g] = hn;
-      if (!is_pad) y[(size_t)(seg.off + t) * ldy + dir * 256 + g] = hn;
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // duration head: sigmoid -> sum over bins -> / speed -> round-half-even -> clamp(min 1)   (kmodel.py:98-103,115)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void duration_kernel(const float* __restrict__ logits, int ld, int nbins, const int* __restrict__ row2seg,
@@ -378,12 +329,6 @@ cudaError_t launch_attention(const float* qkv, float* ctx, const Seg* segs, int 
   if (max_len > 32 * ATT_MAXK) return cudaErrorInvalidValue;
   dim3 grid((max_len + ATT_QW - 1) / ATT_QW, heads, nseg);
   attention_kernel<<<grid, ATT_QW * 32, 0, s>>>(qkv, ctx, segs, heads);
-  return launched();
-}
-cudaError_t launch_lstm(const float* gx, const float* whhT, const float* bias, float* y, int ldy, const LstmSeg* segs, int nseg, cudaStream_t s) {
-  if (nseg <= 0) return cudaSuccess;
-  dim3 grid(nseg, 2);
-  lstm_kernel<<<grid, 1024, 0, s>>>(gx, whhT, bias, y, ldy, segs);
   return launched();
 }
 cudaError_t launch_duration(const float* logits, int ld, int nbins, const int* row2seg, const float* speeds, float* duration, int* pred_dur,
