@@ -344,22 +344,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
           }
         };
-        {
-          // ping-pong: the loads of batch n+1 are issued before batch n is transformed
-          float va[NB][8], vb[NB][8];
-          bool oka[NB], okb[NB];
-          const int step = NB * rpp;
+        // interior tiles (every slab row inside the utterance, full 8-channel chunk): straight-line code, no per-row predicates,
+        // four rows (eight 16-B loads) in flight per thread.  Edge tiles of an utterance take the generic path below.
+        const int row_lo = tile.t0 - p.pad;
+        const bool interior = p.in_shr == 0 && row_lo >= 0 && row_lo + pl.SR <= seg.in_len && c0 + 8 <= p.Cin && second;
+        if (interior) {
+          const float* src0 = p.x + (size_t)(seg.in_off + row_lo) * p.ldx + c0;
+          auto xform_store = [&](int rr, const float4 q0, const float4 q1) {
+            float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = v[e];
+              if (PRO == PRO_LRELU) x = fmaxf(x, x * p.slope);
+              else if (PRO == PRO_ADAIN_LRELU) { const float wv = fmaf(x, pA[e], pB[e]); x = fmaxf(wv, wv * p.slope); }
+              else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-pK[e], __cosf(fmaf(x, pA2[e], pB2[e])), fmaf(x, pA[e], pB[e]));
+              v[e] = x;
+            }
+            uint4 o;
+            if (WFMT == 2) {
+              uint4 ol;
+              float hi[8], lo[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float xs = fminf(fmaxf(v[e] * SPLIT_SA, -65504.f), 65504.f);
+                hi[e] = __half2float(__float2half_rn(xs));
+                lo[e] = xs - hi[e];
+              }
+              o.x = pack_f16_nosat(hi[0], hi[1]); o.y = pack_f16_nosat(hi[2], hi[3]); o.z = pack_f16_nosat(hi[4], hi[5]); o.w = pack_f16_nosat(hi[6], hi[7]);
+              ol.x = pack_f16_nosat(lo[0], lo[1]); ol.y = pack_f16_nosat(lo[2], lo[3]); ol.z = pack_f16_nosat(lo[4], lo[5]); ol.w = pack_f16_nosat(lo[6], lo[7]);
+              *reinterpret_cast<uint4*>(slab + lo_off + (size_t)rr * 16) = ol;
+            } else if (WFMT == 1) {
+              if (PRO >= PRO_ADAIN_LRELU) { o.x = pack_f16_nosat(v[0], v[1]); o.y = pack_f16_nosat(v[2], v[3]); o.z = pack_f16_nosat(v[4], v[5]); o.w = pack_f16_nosat(v[6], v[7]); }
+              else { o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]); }
+            } else { o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]); }
+            *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
+          };
           int r = r0;
-          load_batch(r, va, oka);
-          for (;;) {
-            if (r + step < pl.SR) load_batch(r + step, vb, okb);
+          for (; r + 3 * rpp < pl.SR; r += 4 * rpp) {
+            float4 qa[4], qb[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const float* sp = src0 + (size_t)(r + h * rpp) * p.ldx;
+              qa[h] = __ldg(reinterpret_cast<const float4*>(sp));
+              qb[h] = __ldg(reinterpret_cast<const float4*>(sp + 4));
+            }
+#pragma unroll
+            for (int h = 0; h < 4; ++h) xform_store(r + h * rpp, qa[h], qb[h]);
+          }
+          for (; r < pl.SR; r += rpp) {
+            const float* sp = src0 + (size_t)r * p.ldx;
+            xform_store(r, __ldg(reinterpret_cast<const float4*>(sp)), __ldg(reinterpret_cast<const float4*>(sp + 4)));
+          }
+        } else {
+          float va[NB][8];
+          bool oka[NB];
+#pragma unroll 1
+          for (int r = r0; r < pl.SR; r += NB * rpp) {
+            load_batch(r, va, oka);
             finish_batch(r, va, oka);
-            r += step;
-            if (r >= pl.SR) break;
-            if (r + step < pl.SR) load_batch(r + step, va, oka);
-            finish_batch(r, vb, okb);
-            r += step;
-            if (r >= pl.SR) break;
           }
         }
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
