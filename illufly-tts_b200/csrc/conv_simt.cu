@@ -221,11 +221,15 @@ cudaError_t launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
   if (a.ntiles <= 0) return cudaSuccess;
   const int CinR = (a.Cin + 3) & ~3;
   const size_t dyn = (a.pro >= PRO_ADAIN_LRELU) ? (size_t)5 * CinR * sizeof(float) : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};          // cudaFuncSetAttribute is per device
+  int dev = 0;
+  cudaError_t ed = cudaGetDevice(&dev);
+  if (ed != cudaSuccess) return ed;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   dim3 grid(a.ntiles, (a.Cout + BN - 1) / BN);
   conv_simt_kernel<<<grid, NT, dyn, s>>>(a);

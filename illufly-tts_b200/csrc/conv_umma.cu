@@ -348,7 +348,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         // four rows (eight 16-B loads) in flight per thread.  Edge tiles of an utterance take the generic path below.
         const int row_lo = tile.t0 - p.pad;
         const bool interior = p.in_shr == 0 && row_lo >= 0 && row_lo + pl.SR <= seg.in_len && c0 + 8 <= p.Cin && second;
-        if (interior) {
+        if (c0 >= p.Cin) {                      // padding channels of the last K chunk: zeros, no loads
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          for (int r = r0; r < pl.SR; r += rpp) {
+            *reinterpret_cast<uint4*>(slab + (size_t)r * 16) = z;
+            if (WFMT == 2) *reinterpret_cast<uint4*>(slab + lo_off + (size_t)r * 16) = z;
+          }
+        } else if (interior) {
           const float* src0 = p.x + (size_t)(seg.in_off + row_lo) * p.ldx + c0;
           auto xform_store = [&](int rr, const float4 q0, const float4 q1) {
             float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
@@ -672,7 +678,8 @@ void pads(int Cin, int Cout, bool split, int& cin_pad, int& cout_pad, int& BN) {
   else { cout_pad = round_up(Cout, bnmax); BN = bnmax; }
 }
 
-int g_num_sms = 0;
+int g_num_sms[64] = {0};          // per device
+bool g_attr_set[64] = {false};    // cudaFuncSetAttribute is per device
 
 bool make_plan(const ConvArgs& a, Plan& pl) {
   int cin_pad, cout_pad, BN;
@@ -768,14 +775,21 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
       {conv_umma_kernel<PRO_LRELU, 0>, conv_umma_kernel<PRO_LRELU, 1>, conv_umma_kernel<PRO_LRELU, 2>},
       {conv_umma_kernel<PRO_ADAIN_LRELU, 0>, conv_umma_kernel<PRO_ADAIN_LRELU, 1>, conv_umma_kernel<PRO_ADAIN_LRELU, 2>},
       {conv_umma_kernel<PRO_ADAIN_SNAKE, 0>, conv_umma_kernel<PRO_ADAIN_SNAKE, 1>, conv_umma_kernel<PRO_ADAIN_SNAKE, 2>}};
-  static bool attr_set = false;
-  if (!attr_set) {
+  int dev = 0;
+  {
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  }
+  if (!g_attr_set[dev]) {
     for (int i = 0; i < 4; ++i)
       for (int j = 0; j < 3; ++j) {
         cudaError_t e = cudaFuncSetAttribute(table[i][j], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
       }
-    attr_set = true;
+    cudaError_t e = cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    g_attr_set[dev] = true;
   }
   if (a.pro < 0 || a.pro > 3 || a.wfmt < 0 || a.wfmt > 2) return cudaErrorInvalidValue;
   static int dbg = -1;
@@ -789,14 +803,7 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   }
   u.prof = prof_on ? prof_buf : nullptr;
   const KernelFn kernel = table[a.pro][a.wfmt];
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-  }
-  const int ncta = u.p.items < g_num_sms ? u.p.items : g_num_sms;      // persistent: one CTA per SM
+  const int ncta = u.p.items < g_num_sms[dev] ? u.p.items : g_num_sms[dev];      // persistent: one CTA per SM
   u.p.per_cta = (u.p.items + ncta - 1) / ncta;
   const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
   kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);

@@ -10,10 +10,14 @@ namespace ttsb {
 __constant__ float c_cos20[20];
 __constant__ float c_sin20[20];
 __constant__ float c_hann20[20];
-static bool g_tables_ready = false;
+static bool g_tables_ready[64] = {false};     // __constant__ memory is per device
 
 static cudaError_t ensure_tables() {
-  if (g_tables_ready) return cudaSuccess;
+  int dev = 0;
+  cudaError_t ed = cudaGetDevice(&dev);
+  if (ed != cudaSuccess) return ed;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (g_tables_ready[dev]) return cudaSuccess;
   float c[20], s[20], w[20];
   for (int i = 0; i < 20; ++i) {
     const double a = 2.0 * M_PI * (double)i / 20.0;
@@ -26,7 +30,7 @@ static cudaError_t ensure_tables() {
   if ((e = cudaMemcpyToSymbol(c_cos20, c, sizeof(c))) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(c_sin20, s, sizeof(s))) != cudaSuccess) return e;
   if ((e = cudaMemcpyToSymbol(c_hann20, w, sizeof(w))) != cudaSuccess) return e;
-  g_tables_ready = true;
+  g_tables_ready[dev] = true;
   return cudaSuccess;
 }
 
