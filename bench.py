@@ -250,8 +250,14 @@ def main():
         dom = "conv_tensor" if prof_acc.get("conv_tensor", {}).get("launches", 0) else "conv_fp32"
         p = prof_acc[dom]
         ach = p["flops"] / (p["ms"] * 1e-3) / 1e12 if p["ms"] > 0 else 0.0
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", "r01g_traffic.json")
+        if dom == "conv_tensor" and os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic, traffic_note = tj["dram_bytes_per_launch_mean"], tj["source"]
         roofline = dict(bound="tensor", kernel=("conv_umma_kernel (tcgen05 implicit-GEMM Conv1d)" if dom == "conv_tensor" else "conv_simt_kernel (fp32 FFMA implicit-GEMM Conv1d)"),
-                        achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=ach / peaks["tf_sustained"], traffic=None,
+                        achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=ach / peaks["tf_sustained"], traffic=traffic, traffic_note=traffic_note,
                         peak_source=f"bf16 sustained, {peaks['source']}", launches_per_step=p["launches"] / args.steps,
                         avg_launch_ms=p["ms"] / max(p["launches"], 1), share_of_step=p["ms"] / max(dev_ms, 1e-9))
         hbm = {}
