@@ -22,6 +22,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace ttsb {
 
 namespace {
@@ -31,7 +33,8 @@ constexpr int KCH = 64;                 // channels per weight stage
 constexpr int NPW = 8;                  // producer / epilogue warps
 constexpr int NPROD = NPW * 32;
 constexpr int NEPI = 128;               // 4 epilogue warps (one per TMEM lane quadrant)
-constexpr int NTHREADS = NPROD + 64 + NEPI;   // producers (0-7), weight loader (8), MMA issuer (9), epilogue (10-13)
+constexpr int NTHREADS = NPROD + 64 + NEPI + 32;   // producers (0-7), weight loader (8), MMA issuer (9), epilogue (10-13), row loader (14)
+constexpr int MAXRAW = 8;               // slots of the raw-row ring
 constexpr int MAXSTAGE = 8;
 // split-fp16 mode: operands are pre-scaled by powers of two so that the low halves stay in fp16's normal range
 constexpr float SPLIT_SA = 16.f, SPLIT_SW = 256.f;
@@ -41,7 +44,8 @@ constexpr uint32_t SPIN_LIMIT = 40u * 1000u * 1000u;
 
 struct Plan {
   int BN, KS, nsc, SR, kcn, tmem_cols, ntile_n, nstage, items, per_cta, split, acc_cols;
-  uint32_t off_bar, off_stats, off_par, off_stg, off_slab, slab_bytes, off_w, wstage_bytes, smem_bytes;
+  int nraw, rch;                    // raw-row ring: slots and rows per slot (0 slots = ring disabled)
+  uint32_t off_bar, off_stats, off_par, off_stg, off_slab, slab_bytes, off_w, wstage_bytes, smem_bytes, off_raw, raw_bytes;
 };
 
 struct UArgs {
@@ -200,6 +204,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   auto bar_slab_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 2 + b); };
   auto bar_acc_full = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 4 + b); };
   auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 6 + b); };
+  auto bar_raw_full = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 8 + b); };
+  auto bar_raw_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 8 + MAXRAW + b); };
   double* s_sum = reinterpret_cast<double*>(smem + pl.off_stats);   // [4 row quadrants][256], double: the running sums
   double* s_sq = s_sum + 4 * 256;                                   // must not depend on how tiles are dealt to CTAs
   float* s_par = reinterpret_cast<float*>(smem + pl.off_par);       // [5][cin_pad]: mean, a, b, alpha, 1/alpha
@@ -217,6 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       mbar_init(bar_slab_full(b), NPROD); mbar_init(bar_slab_empty(b), 1);
       mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), NEPI);
     }
+    for (int b = 0; b < MAXRAW; ++b) { mbar_init(bar_raw_full(b), 1); mbar_init(bar_raw_empty(b), NPROD); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int c = tid; c < 2048; c += NTHREADS) s_sum[c] = 0.0;
@@ -234,8 +241,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     const int planes = pl.KS >> 3;
     const int rpp = NPROD / planes;                    // rows per pass
     const int pln = tid % planes, r0 = tid / planes;
-    int cur_seg = -1;
+    int cur_seg = -1, par_c0 = -1, par_seg = -1;
+    float pA[8], pB[8], pA2[8], pB2[8], pK[8];
     uint32_t g = 0;                                    // running slab counter of this CTA
+    uint32_t rslot = 0, rphase = 0;                    // position in the raw-row ring
     long long t_wait = 0;
     const long long t_start = clock64();
     for (int item = item0; item < item1; ++item) {
@@ -265,8 +274,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         const uint32_t b = g & 1u;
         mbar_wait_t(bar_slab_empty(b), ((g >> 1) & 1u) ^ 1u, t_wait);
         const int c0 = sc * pl.KS + pln * 8;
-        float pA[8], pB[8], pA2[8], pB2[8], pK[8];
-        if (PRO >= PRO_ADAIN_LRELU) {
+        if (PRO >= PRO_ADAIN_LRELU && (c0 != par_c0 || tile.seg != par_seg)) {      // one slab per tile: the constants stay in registers
+          par_c0 = c0; par_seg = tile.seg;
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             pA[e] = s_par[c0 + e]; pB[e] = s_par[cpad + c0 + e];
@@ -348,7 +357,71 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         // four rows (eight 16-B loads) in flight per thread.  Edge tiles of an utterance take the generic path below.
         const int row_lo = tile.t0 - p.pad;
         const bool interior = p.in_shr == 0 && row_lo >= 0 && row_lo + pl.SR <= seg.in_len && c0 + 8 <= p.Cin && second;
-        if (c0 >= p.Cin) {                      // padding channels of the last K chunk: zeros, no loads
+        auto xform_store = [&](int rr, const float4 q0, const float4 q1) {
+          float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float x = v[e];
+            if (PRO == PRO_LRELU) x = fmaxf(x, x * p.slope);
+            else if (PRO == PRO_ADAIN_LRELU) { const float wv = fmaf(x, pA[e], pB[e]); x = fmaxf(wv, wv * p.slope); }
+            else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-pK[e], __cosf(fmaf(x, pA2[e], pB2[e])), fmaf(x, pA[e], pB[e]));
+            v[e] = x;
+          }
+          uint4 o;
+          if (WFMT == 2) {
+            uint4 ol;
+            float hi[8], lo[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float xs = fminf(fmaxf(v[e] * SPLIT_SA, -65504.f), 65504.f);
+              hi[e] = __half2float(__float2half_rn(xs));
+              lo[e] = xs - hi[e];
+            }
+            o.x = pack_f16_nosat(hi[0], hi[1]); o.y = pack_f16_nosat(hi[2], hi[3]); o.z = pack_f16_nosat(hi[4], hi[5]); o.w = pack_f16_nosat(hi[6], hi[7]);
+            ol.x = pack_f16_nosat(lo[0], lo[1]); ol.y = pack_f16_nosat(lo[2], lo[3]); ol.z = pack_f16_nosat(lo[4], lo[5]); ol.w = pack_f16_nosat(lo[6], lo[7]);
+            *reinterpret_cast<uint4*>(slab + lo_off + (size_t)rr * 16) = ol;
+          } else if (WFMT == 1) {
+            if (PRO >= PRO_ADAIN_LRELU) { o.x = pack_f16_nosat(v[0], v[1]); o.y = pack_f16_nosat(v[2], v[3]); o.z = pack_f16_nosat(v[4], v[5]); o.w = pack_f16_nosat(v[6], v[7]); }
+            else { o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]); }
+          } else { o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]); }
+          *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
+        };
+        const bool ring = pl.nraw > 0 && p.in_shr == 0 && row_lo >= 0 && row_lo + pl.SR <= seg.in_len;
+        if (ring) {
+          // interior tile: the row loader streams the fp32 rows of this slab through a shared-memory ring with the bulk-copy
+          // engine (no LDG, no L1 queue); the producers only transform ring slot -> 16-bit slab, two rows in flight per thread
+          // (a slot holds 2 * rpp rows)
+          const int nch = (pl.SR + pl.rch - 1) / pl.rch;
+          // groups of four lanes alternate which 16-B half of their 32 B they read first: eight lanes x 16 B at a 32-B stride
+          // would hit every bank group twice
+          const int hf = (tid >> 2) & 1;
+          const int sp_off = r0 * pl.KS + pln * 8;
+          const int row2 = rpp * pl.KS;                     // floats between a thread's two rows of a slot
+          for (int ch = 0; ch < nch; ++ch) {
+            mbar_wait_t(bar_raw_full(rslot), rphase, t_wait);
+            const float* sp = reinterpret_cast<const float*>(smem + pl.off_raw + (size_t)rslot * pl.raw_bytes) + sp_off;
+            const int ra = ch * pl.rch + r0, rb = ra + rpp;
+            const bool hasa = ra < pl.SR, hasb = rb < pl.SR;
+            const float* spb = hasb ? sp + row2 : sp;
+            float4 ax = *reinterpret_cast<const float4*>(sp + 4 * hf);
+            float4 ay = *reinterpret_cast<const float4*>(sp + 4 * (hf ^ 1));
+            float4 bx = *reinterpret_cast<const float4*>(spb + 4 * hf);
+            float4 by = *reinterpret_cast<const float4*>(spb + 4 * (hf ^ 1));
+            float4 a0 = hf ? ay : ax, a1 = hf ? ax : ay, b0 = hf ? by : bx, b1 = hf ? bx : by;
+            if (tailc) {        // channels past Cin: the ring holds stale bytes there and the operand must be zero
+              float* t0 = &a0.x; float* t1 = &a1.x; float* t2 = &b0.x; float* t3 = &b1.x;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (c0 + e >= p.Cin) { t0[e] = 0.f; t2[e] = 0.f; }
+                if (c0 + 4 + e >= p.Cin) { t1[e] = 0.f; t3[e] = 0.f; }
+              }
+            }
+            if (hasa) xform_store(ra, a0, a1);
+            if (hasb) xform_store(rb, b0, b1);
+            mbar_arrive(bar_raw_empty(rslot));      // this thread is done reading the slot
+            if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
+          }
+        } else if (c0 >= p.Cin) {                      // padding channels of the last K chunk: zeros, no loads
           const uint4 z = make_uint4(0u, 0u, 0u, 0u);
           for (int r = r0; r < pl.SR; r += rpp) {
             *reinterpret_cast<uint4*>(slab + (size_t)r * 16) = z;
@@ -356,35 +429,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           }
         } else if (interior) {
           const float* src0 = p.x + (size_t)(seg.in_off + row_lo) * p.ldx + c0;
-          auto xform_store = [&](int rr, const float4 q0, const float4 q1) {
-            float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = v[e];
-              if (PRO == PRO_LRELU) x = fmaxf(x, x * p.slope);
-              else if (PRO == PRO_ADAIN_LRELU) { const float wv = fmaf(x, pA[e], pB[e]); x = fmaxf(wv, wv * p.slope); }
-              else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-pK[e], __cosf(fmaf(x, pA2[e], pB2[e])), fmaf(x, pA[e], pB[e]));
-              v[e] = x;
-            }
-            uint4 o;
-            if (WFMT == 2) {
-              uint4 ol;
-              float hi[8], lo[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float xs = fminf(fmaxf(v[e] * SPLIT_SA, -65504.f), 65504.f);
-                hi[e] = __half2float(__float2half_rn(xs));
-                lo[e] = xs - hi[e];
-              }
-              o.x = pack_f16_nosat(hi[0], hi[1]); o.y = pack_f16_nosat(hi[2], hi[3]); o.z = pack_f16_nosat(hi[4], hi[5]); o.w = pack_f16_nosat(hi[6], hi[7]);
-              ol.x = pack_f16_nosat(lo[0], lo[1]); ol.y = pack_f16_nosat(lo[2], lo[3]); ol.z = pack_f16_nosat(lo[4], lo[5]); ol.w = pack_f16_nosat(lo[6], lo[7]);
-              *reinterpret_cast<uint4*>(slab + lo_off + (size_t)rr * 16) = ol;
-            } else if (WFMT == 1) {
-              if (PRO >= PRO_ADAIN_LRELU) { o.x = pack_f16_nosat(v[0], v[1]); o.y = pack_f16_nosat(v[2], v[3]); o.z = pack_f16_nosat(v[4], v[5]); o.w = pack_f16_nosat(v[6], v[7]); }
-              else { o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]); }
-            } else { o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]); }
-            *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
-          };
           int r = r0;
           for (; r + 3 * rpp < pl.SR; r += 4 * rpp) {
             float4 qa[4], qb[4];
@@ -504,6 +548,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       if (u.prof && lane == 0) {
         long long* pp = u.prof + blockIdx.x * 16;
         pp[2] = clock64() - t_start; pp[3] = tw_slab; pp[4] = tw_acc; pp[5] = tw_w;
+      }
+    }
+  } else if (warp == NPW + 2 + NEPI / 32) {
+    // =================== row loader: fp32 activation rows -> raw ring (bulk-copy engine) ===================
+    if (pl.nraw > 0) {
+      uint32_t rslot = 0, rphase = 0;
+      const int nch = (pl.SR + pl.rch - 1) / pl.rch;
+      for (int item = item0; item < item1; ++item) {
+        const Tile tile = p.tiles[item % p.ntiles];
+        const Seg seg = p.segs[tile.seg];
+        const int row_lo = tile.t0 - p.pad;
+        if (!(p.in_shr == 0 && row_lo >= 0 && row_lo + pl.SR <= seg.in_len)) continue;      // edge tile: producers load it themselves
+        for (int sc = 0; sc < pl.nsc; ++sc) {
+          const int cbase = sc * pl.KS;
+          int nfl = p.ldx - cbase;                        // floats of this channel slice present in a row of x
+          nfl = nfl > pl.KS ? pl.KS : nfl;
+          const uint32_t row_bytes = (uint32_t)nfl * 4u;
+          const bool contiguous = p.ldx == pl.KS;         // whole rows: the chunk is one contiguous block
+          for (int ch = 0; ch < nch; ++ch) {
+            const uint32_t slot = rslot;
+            mbar_wait(bar_raw_empty(slot), rphase ^ 1u);
+            if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
+            const int rows_n = min(pl.rch, pl.SR - ch * pl.rch);
+            const float* src = p.x + (size_t)(seg.in_off + row_lo + ch * pl.rch) * p.ldx + cbase;
+            const uint32_t dst = smem_u32(smem + pl.off_raw + (size_t)slot * pl.raw_bytes);
+            if (lane == 0) mbar_expect_tx(bar_raw_full(slot), (uint32_t)rows_n * row_bytes);
+            __syncwarp();                                  // the byte count is registered before any copy can complete
+            if (contiguous) {
+              if (lane == 0) bulk_g2s(dst, src, (uint32_t)rows_n * row_bytes, bar_raw_full(slot));
+            } else {                                       // strided rows: one copy per row, the lanes issue them side by side
+              for (int r = lane; r < rows_n; r += 32)
+                bulk_g2s(dst + (uint32_t)r * (uint32_t)pl.KS * 4u, src + (size_t)r * p.ldx, row_bytes, bar_raw_full(slot));
+            }
+          }
+        }
       }
     }
   } else {
@@ -697,7 +776,7 @@ bool make_plan(const ConvArgs& a, Plan& pl) {
   while (tc < 2 * pl.acc_cols) tc <<= 1;           // two accumulator buffers
   pl.tmem_cols = tc;
   uint32_t off = 16;
-  pl.off_bar = off; off += 8u * (2 * MAXSTAGE + 8);
+  pl.off_bar = off; off += 8u * (2 * MAXSTAGE + 8 + 2 * MAXRAW);
   off = (off + 15u) & ~15u;
   pl.off_stats = off; off += 2048 * 8;
   pl.off_par = off; off += a.pro >= PRO_ADAIN_LRELU ? 5u * cin_pad * 4u : 0u;
@@ -709,8 +788,27 @@ bool make_plan(const ConvArgs& a, Plan& pl) {
   pl.slab_bytes = (pl.slab_bytes + 127u) & ~127u;
   pl.wstage_bytes = (uint32_t)BN * KCH * 2u * (pl.split ? 2u : 1u);
   pl.off_w = pl.off_slab + 2 * pl.slab_bytes;
-  pl.nstage = MAXSTAGE;
-  while (pl.nstage > 2 && pl.off_w + pl.nstage * pl.wstage_bytes > 227u * 1024u) --pl.nstage;
+  // shared memory left after two weight stages goes first to the raw-row ring (>= 2 slots or none), then to more weight stages
+  const uint32_t limit = 227u * 1024u;
+  pl.nstage = 2;
+  pl.nraw = 0; pl.rch = 32; pl.raw_bytes = 0;
+  const bool ring_ok = a.in_shr == 0 && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 && getenv("TTSB_UMMA_NORING") == nullptr &&
+                       (getenv("TTSB_UMMA_RINGALL") != nullptr || a.ldx == pl.KS);
+  if (ring_ok) {
+    static const int env_nraw = getenv("TTSB_UMMA_NRAW") ? atoi(getenv("TTSB_UMMA_NRAW")) : 3;
+    for (int rch : {2 * NPROD / (pl.KS / 8)}) {        // two rows per producer thread and slot: 16 KB slots
+      const uint32_t slot = (uint32_t)rch * pl.KS * 4u;
+      const uint32_t used = pl.off_w + 2 * pl.wstage_bytes;
+      if (used + 2 * slot <= limit) {
+        pl.rch = rch; pl.raw_bytes = slot;
+        pl.nraw = (int)std::min<uint32_t>((limit - used) / slot, (uint32_t)std::min(env_nraw, MAXRAW));
+        break;
+      }
+    }
+  }
+  pl.off_raw = pl.off_w;                       // ring first, weight stages after it
+  pl.off_w = pl.off_raw + pl.nraw * pl.raw_bytes;
+  while (pl.nstage < MAXSTAGE && pl.off_w + (pl.nstage + 1) * pl.wstage_bytes <= limit) ++pl.nstage;
   pl.smem_bytes = pl.off_w + pl.nstage * pl.wstage_bytes;
   pl.items = a.ntiles * pl.ntile_n;
   return pl.smem_bytes <= 227u * 1024u;
@@ -806,14 +904,27 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   const int ncta = u.p.items < g_num_sms[dev] ? u.p.items : g_num_sms[dev];      // persistent: one CTA per SM
   u.p.per_cta = (u.p.items + ncta - 1) / ncta;
   const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
+  static cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (prof_on) {
+    if (!pe0) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
+    cudaEventRecord(pe0, s);
+  }
   kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
+  if (prof_on) cudaEventRecord(pe1, s);
   if (prof_on) {      // diagnostic mode: synchronous, prints the mean cycle split of the roles for every launch
     static long long host[16 * 256];
     if (cudaStreamSynchronize(s) == cudaSuccess && cudaMemcpy(host, prof_buf, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost) == cudaSuccess) {
       double m[9] = {0};
-      for (int c = 0; c < grid; ++c) for (int i = 0; i < 9; ++i) m[i] += (double)host[c * 16 + i] / grid;
-      fprintf(stderr, "umma pro=%d fmt=%d Cin=%d Cout=%d k=%d dil=%d grid=%d items/cta=%.1f | producer %.0f (wait %.0f) | mma %.0f (wait slab %.0f acc %.0f w %.0f) | epilogue %.0f (wait %.0f) cycles\n",
-              a.pro, a.wfmt, a.Cin, a.Cout, a.k, a.dil, grid, m[8], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7]);
+      long long emax = 0, emin = 1LL << 62;
+      for (int c = 0; c < grid; ++c) {
+        for (int i = 0; i < 9; ++i) m[i] += (double)host[c * 16 + i] / grid;
+        emax = host[c * 16 + 6] > emax ? host[c * 16 + 6] : emax;
+        emin = host[c * 16 + 6] < emin ? host[c * 16 + 6] : emin;
+      }
+      float us = 0.f;
+      cudaEventElapsedTime(&us, pe0, pe1);
+      fprintf(stderr, "umma pro=%d fmt=%d Cin=%d Cout=%d k=%d dil=%d grid=%d items/cta=%.1f | producer %.0f (wait %.0f) | mma %.0f (wait slab %.0f acc %.0f w %.0f) | epilogue %.0f (wait %.0f) cycles | epilogue min %lld max %lld | %.1f us\n",
+              a.pro, a.wfmt, a.Cin, a.Cout, a.k, a.dil, grid, m[8], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], emin, emax, us * 1000.f);
     }
   }
   return launched();

@@ -324,7 +324,7 @@ int engine_finalize(Engine& e) {
   const std::string G = "decoder.generator.";
   e.src_lin_w = ld.upload_named(G + "m_source.l_linear.weight");
   e.src_lin_b = ld.upload_named(G + "m_source.l_linear.bias");
-  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, 1) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, 1);
+  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, 0) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, 1);
   if (ok) {
     // noise_convs[0]: Conv1d(22, 256, k12, stride 6, pad 3) over STFT frames == k3/pad1 conv over frames regrouped six at a time
     // ([blocks, 6 x 24] view of the channels-last har buffer): tap in {0,1,2}, slot i in 0..5  <->  original tap j = 6 tap + i - 3

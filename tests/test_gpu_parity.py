@@ -84,6 +84,28 @@ def test_vocoder_only(engine, oracle, precision, tol, snr):
         engine.set_precision(pkg.PRECISION_FP32)
 
 
+def test_vocoder_ragged_lengths(engine, oracle):
+    """generator on a ragged batch: per-utterance InstanceNorm statistics, conv zero padding and STFT reflection at each
+    utterance's own edges (rows of different utterances are adjacent in memory)"""
+    engine.set_precision(pkg.PRECISION_FP32)
+    B, L = 3, 40
+    lens = [40, 7, 23]
+    x, s, f0, noise = vocoder_inputs(B, L)
+    engine.enable_taps(True)
+    try:
+        audio = engine.vocoder(x, s, f0, noise, lengths=lens)
+        har = engine.read_tap("har")
+    finally:
+        engine.enable_taps(False)
+    row = 0
+    for b, Lb in enumerate(lens):
+        n = 60 * Lb + 1
+        assert audio[b].shape == (300 * Lb,)
+        vocoder_check(oracle, x[b:b + 1, :, :Lb], s[b:b + 1], f0[b:b + 1, :Lb], noise[b:b + 1, :300 * Lb], har[row:row + n], audio[b], 1e-3, 60.0,
+                      f"ragged item {b}")
+        row += n
+
+
 def test_forced_durations_and_in_kernel_noise(engine):
     """forced durations drive the frame count; Philox noise path: deterministic for a seed, different across seeds"""
     w = small_batch([9, 14])
