@@ -51,6 +51,7 @@ struct ConvArgs {
   float acc_scale;                     // tensor path: accumulator * acc_scale before bias (undoes the split-mode operand scaling); 0 = 1
   double* ostats; int ld_ostats;       // [nseg][ld_ostats][2]
   const Seg* segs; const Tile* tiles; int ntiles; int tile_rows;
+  uint8_t* xpack; size_t xpack_bytes;  // scratch for the pre-packed split-fp16 operand images of k=1 layers (conv_umma.cu), or null
 };
 
 struct LstmSeg {                       // host-side description of one utterance's recurrence

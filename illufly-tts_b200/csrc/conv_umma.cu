@@ -52,6 +52,7 @@ struct UArgs {
   ConvArgs a;
   Plan p;
   long long* prof;   // optional [grid][16] cycle counters per role (TTSB_UMMA_PROF), else null
+  const uint8_t* xpack;   // pre-packed operand slabs [tile][K chunk][slab image] (pack_split_kernel), else null
   int dbg;     // TTSB_UMMA_DBG (timing experiments only, results become garbage): 1 = producers skip global loads,
                // 2 = epilogue skips global traffic, 4 = no MMA issue; applied to the Snake-prologue variants only
 };
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   if (tid == 0) {
     for (int s = 0; s < MAXSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_slab_full(b), NPROD); mbar_init(bar_slab_empty(b), 1);
+      mbar_init(bar_slab_full(b), u.xpack ? 1 : NPROD); mbar_init(bar_slab_empty(b), 1);
       mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), NEPI);
     }
     for (int b = 0; b < MAXRAW; ++b) { mbar_init(bar_raw_full(b), 1); mbar_init(bar_raw_empty(b), NPROD); }
@@ -236,7 +237,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   const uint32_t slab0 = smem_u32(smem + pl.off_slab);
   const uint32_t w0 = smem_u32(smem + pl.off_w);
 
-  if (warp < NPW) {
+  if (warp < NPW && u.xpack) {
+    // =================== pre-packed operands: the slabs are bulk-copied as they lie in global memory ===================
+    if (tid == 0) {
+      uint32_t g = 0;
+      long long t_wait = 0;
+      const long long t_start = clock64();
+      for (int item = item0; item < item1; ++item) {
+        const uint8_t* src = u.xpack + (size_t)(item % p.ntiles) * pl.nsc * pl.slab_bytes;
+        for (int sc = 0; sc < pl.nsc; ++sc, ++g) {
+          const uint32_t b = g & 1u;
+          mbar_wait_t(bar_slab_empty(b), ((g >> 1) & 1u) ^ 1u, t_wait);
+          mbar_expect_tx(bar_slab_full(b), pl.slab_bytes);
+          bulk_g2s(slab0 + b * pl.slab_bytes, src + (size_t)sc * pl.slab_bytes, pl.slab_bytes, bar_slab_full(b));
+        }
+      }
+      if (u.prof) { u.prof[blockIdx.x * 16 + 0] = clock64() - t_start; u.prof[blockIdx.x * 16 + 1] = t_wait; }
+    }
+  } else if (warp < NPW) {
     // =================== producers: build the 16-bit operand slabs ===================
     const int planes = pl.KS >> 3;
     const int rpp = NPROD / planes;                    // rows per pass
@@ -748,6 +766,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   if (warp == NPW + 1) tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
 }
 
+// Split-fp16 operand images of a k=1 layer's input, one per (row tile, 64-channel chunk), laid out exactly like the kernel's
+// shared-memory slab ([hi | lo][8-channel plane][SR rows][8 x fp16]): the GEMM then bulk-copies them instead of converting
+// the same rows again for every Cout tile (the text-side GEMMs were producer bound: 18 Cout tiles re-converted each row tile).
+__global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict__ x, int ldx, int Cin, const Seg* __restrict__ segs,
+                                                         const Tile* __restrict__ tiles, int nsc, int SR, uint32_t slab_bytes,
+                                                         uint8_t* __restrict__ out) {
+  const Tile tile = tiles[blockIdx.x];
+  const Seg seg = segs[tile.seg];
+  const int sc = blockIdx.y;
+  uint8_t* blk = out + ((size_t)blockIdx.x * nsc + sc) * slab_bytes;
+  const size_t lo_off = (size_t)8 * SR * 16;
+  for (int idx = threadIdx.x; idx < 8 * SR; idx += blockDim.x) {
+    const int r = idx % SR, pln = idx / SR;
+    const int c0 = sc * 64 + pln * 8;
+    const int t = tile.t0 + r;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (r < BM && t < seg.in_len && c0 < Cin) {
+      const float* src = x + (size_t)(seg.in_off + t) * ldx + c0;
+      if (c0 + 8 <= Cin && (ldx & 3) == 0) {
+        const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src + 4));
+        v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (c0 + e < Cin) v[e] = __ldg(src + e);
+      }
+    }
+    float hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xs = fminf(fmaxf(v[e] * SPLIT_SA, -65504.f), 65504.f);
+      hi[e] = __half2float(__float2half_rn(xs));
+      lo[e] = xs - hi[e];
+    }
+    uint4 oh, ol;
+    oh.x = pack_f16_nosat(hi[0], hi[1]); oh.y = pack_f16_nosat(hi[2], hi[3]); oh.z = pack_f16_nosat(hi[4], hi[5]); oh.w = pack_f16_nosat(hi[6], hi[7]);
+    ol.x = pack_f16_nosat(lo[0], lo[1]); ol.y = pack_f16_nosat(lo[2], lo[3]); ol.z = pack_f16_nosat(lo[4], lo[5]); ol.w = pack_f16_nosat(lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(blk + (size_t)idx * 16) = oh;
+    *reinterpret_cast<uint4*>(blk + lo_off + (size_t)idx * 16) = ol;
+  }
+}
+
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 void pads(int Cin, int Cout, bool split, int& cin_pad, int& cout_pad, int& BN) {
@@ -900,6 +961,16 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     if (prof_on && cudaMalloc(&prof_buf, sizeof(long long) * 16 * 256) != cudaSuccess) prof_on = 0;
   }
   u.prof = prof_on ? prof_buf : nullptr;
+  u.xpack = nullptr;
+  static const bool nopack = getenv("TTSB_UMMA_NOPACK") != nullptr;
+  if (a.xpack && a.wfmt == 2 && a.k == 1 && a.in_shr == 0 && a.pro == PRO_NONE && a.stride == 1 && a.pad == 0 && u.p.ntile_n > 1 && !nopack &&
+      (size_t)a.ntiles * u.p.nsc * u.p.slab_bytes <= a.xpack_bytes && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {
+    pack_split_kernel<<<dim3(a.ntiles, u.p.nsc), 256, 0, s>>>(a.x, a.ldx, a.Cin, a.segs, a.tiles, u.p.nsc, u.p.SR, u.p.slab_bytes, a.xpack);
+    cudaError_t e = launched();
+    if (e != cudaSuccess) return e;
+    u.xpack = a.xpack;
+    u.p.nraw = 0;                     // no row ring in this mode
+  }
   const KernelFn kernel = table[a.pro][a.wfmt];
   const int ncta = u.p.items < g_num_sms[dev] ? u.p.items : g_num_sms[dev];      // persistent: one CTA per SM
   u.p.per_cta = (u.p.items + ncta - 1) / ncta;

@@ -375,6 +375,7 @@ struct Run {
   char* d_tables = nullptr;
   size_t tables_cap = 0;
   double* stats_base = nullptr; size_t stats_cap = 0, stats_off = 0;
+  uint8_t* xpack = nullptr; size_t xpack_bytes = 0;     // scratch of the pre-packed operand images (text-side GEMMs), reused call after call
   explicit Run(Engine& en) : e(en), s(en.stream) {}
 
   template <typename T>
@@ -517,6 +518,16 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   a.out_scale = c.out_scale; a.accumulate = c.accumulate; a.act = c.act; a.act_slope = c.act_slope;
   a.ostats = c.ostats; a.ld_ostats = c.w->Cout;
   a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
+  if (c.exact && a.k == 1 && r.e.precision != TTSB_PRECISION_FP32) {
+    // split-fp16 image of the input: 129-row slabs of 64 channels, hi + lo halves (conv_umma.cu: pack_split_kernel)
+    const size_t need = (size_t)t.ntiles * ((a.cin_pad + 63) / 64) * (2 * 8 * 129 * 16);
+    if (need > r.xpack_bytes) {
+      const size_t cap = need > ((size_t)24 << 20) ? need : ((size_t)24 << 20);
+      uint8_t* pnew = r.alloc<uint8_t>(cap);
+      if (pnew) { r.xpack = pnew; r.xpack_bytes = cap; }
+    }
+    a.xpack = r.xpack; a.xpack_bytes = r.xpack_bytes;
+  }
   if (c.pro >= PRO_ADAIN_LRELU && (!c.pstats || !c.gb)) { set_error("internal: AdaIN prologue without statistics"); return TTSB_E_INVALID; }
   const double rows = (double)t.out_rows;
   const double fl = 2.0 * rows * a.Cin * a.Cout * a.k;

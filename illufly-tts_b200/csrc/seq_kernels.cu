@@ -118,39 +118,40 @@ __global__ void fill_style_kernel(const float* __restrict__ style, int ld_style,
 // scores/softmax exactly two-pass (max, exp, sum) like torch.softmax; 1/sqrt(64) applied to the scores.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int ATT_MAXK = 16;   // keys per lane: T <= 512
-constexpr int ATT_QW = 16;     // queries (warps) per CTA
-constexpr int ATT_KC = 128;    // keys per shared-memory chunk
+constexpr int ATT_QB = 32;     // queries per CTA (8 warps x 4 queries)
+constexpr int ATT_KC = 64;     // keys per shared-memory chunk
 constexpr int ATT_LD = 68;     // padded row (floats): 16-B aligned, conflict-free for LDS.128 across rows
 
-// One CTA = 16 queries of one (utterance, head).  K and V are staged through shared memory in chunks of 128 keys
-// (coalesced loads, every key row is read once per CTA instead of once per warp); lane = key for the scores,
-// lane = output dimension pair for P V.  Two-pass softmax (max, exp, sum) as torch.softmax.
-__global__ void __launch_bounds__(ATT_QW * 32) attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, const Seg* __restrict__ segs, int heads) {
-  __shared__ __align__(16) float kv[ATT_KC][ATT_LD];
+// One CTA = 32 queries of one (utterance, head); every warp owns four of them and works on all four at once, so one K or V
+// element read from shared memory feeds four FMAs.  K and V pass through one 64-key staging buffer (coalesced loads); the
+// scores of the CTA live in shared memory [32][len] between the phases.  Two-pass softmax (max, exp, sum) as torch.softmax,
+// every sum in a fixed order: lane = key for the scores, lane = output dimension pair for P V.
+// (r01: one CTA per 16 queries with the query and its scores in registers ran at one CTA per SM: 107 us per layer.)
+__global__ void __launch_bounds__(256) attention_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, const Seg* __restrict__ segs, int heads,
+                                                        int ld_s) {
+  extern __shared__ __align__(16) float att_smem[];
+  float (*kv)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);                  // [ATT_KC][ATT_LD]
+  float (*qs)[64] = reinterpret_cast<float (*)[64]>(att_smem + ATT_KC * ATT_LD);       // [ATT_QB][64]
+  float* S = att_smem + ATT_KC * ATT_LD + ATT_QB * 64;                                  // [ATT_QB][ld_s]
   const Seg seg = segs[blockIdx.z];
   const int head = blockIdx.y;
-  const int q0 = blockIdx.x * ATT_QW;
-  if (q0 >= seg.in_len) return;
+  const int q0 = blockIdx.x * ATT_QB;
+  const int len = seg.in_len;
+  if (q0 >= len) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qi = q0 + warp;
-  const bool valid = qi < seg.in_len;
   const int H = heads * 64;
   const int ld = 3 * H;
-  const int len = seg.in_len;
   const int nchunk = (len + ATT_KC - 1) / ATT_KC;
-  float q[64];
-  if (valid) {
-    const float* qrow = qkv + (size_t)(seg.in_off + qi) * ld + head * 64;
-#pragma unroll
-    for (int d = 0; d < 64; d += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(qrow + d);
-      q[d] = t.x; q[d + 1] = t.y; q[d + 2] = t.z; q[d + 3] = t.w;
-    }
+  for (int idx = tid; idx < ATT_QB * 16; idx += 256) {             // the CTA's queries
+    const int r = idx >> 4, c4 = idx & 15;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < len) t = *reinterpret_cast<const float4*>(qkv + (size_t)(seg.in_off + q0 + r) * ld + head * 64 + c4 * 4);
+    *reinterpret_cast<float4*>(&qs[r][c4 * 4]) = t;
   }
-  auto stage = [&](int chunk, int col_off) {       // rows [chunk*128, +128) of K (col_off = H) or V (2H) -> shared memory
+  auto stage = [&](int chunk, int col_off) {       // rows [chunk*64, +64) of K (col_off = H) or V (2H) -> shared memory
 #pragma unroll
-    for (int it = 0; it < (ATT_KC * 16) / (ATT_QW * 32); ++it) {
-      const int idx = tid + it * (ATT_QW * 32);
+    for (int it = 0; it < (ATT_KC * 16) / 256; ++it) {
+      const int idx = tid + it * 256;
       const int r = idx >> 4, c4 = idx & 15;
       const int key = chunk * ATT_KC + r;
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -158,70 +159,99 @@ __global__ void __launch_bounds__(ATT_QW * 32) attention_kernel(const float* __r
       *reinterpret_cast<float4*>(&kv[r][c4 * 4]) = t;
     }
   };
-  float sc[ATT_MAXK];
+  const int qw = warp * 4;                          // this warp's queries qw .. qw+3 (rows of qs / S)
+  // ---- scores: S[q][key] = (q . k) / 8 --------------------------------------------------------------------
+  for (int chunk = 0; chunk < nchunk; ++chunk) {
+    __syncthreads();
+    stage(chunk, H);
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < ATT_MAXK; ++i) sc[i] = -INFINITY;
-  float mx = -INFINITY;
+    for (int j = 0; j < ATT_KC / 32; ++j) {
+      const int kl = j * 32 + lane;
+      const int key = chunk * ATT_KC + kl;
+      if (chunk * ATT_KC + j * 32 < len) {          // warp-uniform
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-  for (int chunk = 0; chunk < ATT_MAXK / 4; ++chunk) {
-    if (chunk < nchunk) {
-      __syncthreads();
-      stage(chunk, H);
-      __syncthreads();
-      if (valid) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kl = j * 32 + lane;
-          if (chunk * ATT_KC + kl < len) {
-            float a = 0.f;
-#pragma unroll
-            for (int d = 0; d < 64; d += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(&kv[kl][d]);
-              a = fmaf(q[d], t.x, a); a = fmaf(q[d + 1], t.y, a); a = fmaf(q[d + 2], t.z, a); a = fmaf(q[d + 3], t.w, a);
-            }
-            sc[chunk * 4 + j] = a * 0.125f;
-            mx = fmaxf(mx, sc[chunk * 4 + j]);
-          }
+        for (int d = 0; d < 64; d += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(&kv[kl][d]);
+          const float4 x0 = *reinterpret_cast<const float4*>(&qs[qw][d]);
+          const float4 x1 = *reinterpret_cast<const float4*>(&qs[qw + 1][d]);
+          const float4 x2 = *reinterpret_cast<const float4*>(&qs[qw + 2][d]);
+          const float4 x3 = *reinterpret_cast<const float4*>(&qs[qw + 3][d]);
+          a0 = fmaf(x0.x, t.x, a0); a0 = fmaf(x0.y, t.y, a0); a0 = fmaf(x0.z, t.z, a0); a0 = fmaf(x0.w, t.w, a0);
+          a1 = fmaf(x1.x, t.x, a1); a1 = fmaf(x1.y, t.y, a1); a1 = fmaf(x1.z, t.z, a1); a1 = fmaf(x1.w, t.w, a1);
+          a2 = fmaf(x2.x, t.x, a2); a2 = fmaf(x2.y, t.y, a2); a2 = fmaf(x2.z, t.z, a2); a2 = fmaf(x2.w, t.w, a2);
+          a3 = fmaf(x3.x, t.x, a3); a3 = fmaf(x3.y, t.y, a3); a3 = fmaf(x3.z, t.z, a3); a3 = fmaf(x3.w, t.w, a3);
+        }
+        if (key < len) {
+          S[(qw + 0) * ld_s + key] = a0 * 0.125f; S[(qw + 1) * ld_s + key] = a1 * 0.125f;
+          S[(qw + 2) * ld_s + key] = a2 * 0.125f; S[(qw + 3) * ld_s + key] = a3 * 0.125f;
         }
       }
     }
   }
-  mx = warp_max(mx);
-  float sum = 0.f;
+  __syncwarp();
+  // ---- softmax of the warp's four rows: lane i owns keys i, i+32, ... (ascending), then a butterfly over the lanes -----
 #pragma unroll
-  for (int i = 0; i < ATT_MAXK; ++i) {
-    const float e = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - mx);
-    sc[i] = e;
-    sum += e;
+  for (int qq = 0; qq < 4; ++qq) {
+    float* row = S + (qw + qq) * ld_s;
+    float mx = -INFINITY;
+    for (int k = lane; k < len; k += 32) mx = fmaxf(mx, row[k]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < len; k += 32) {
+      const float e = expf(row[k] - mx);
+      row[k] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    for (int k = lane; k < len; k += 32) row[k] *= inv;
   }
-  sum = warp_sum(sum);
-  const float inv = valid ? 1.0f / sum : 0.f;
-  float o0 = 0.f, o1 = 0.f;
+  // ---- P V: lane = output dimensions (lane, lane+32), keys in ascending order ---------------------------------
+  float o[4][2];
 #pragma unroll
-  for (int chunk = 0; chunk < ATT_MAXK / 4; ++chunk) {
-    if (chunk < nchunk) {
-      __syncthreads();
-      stage(chunk, 2 * H);
-      __syncthreads();
+  for (int qq = 0; qq < 4; ++qq) { o[qq][0] = 0.f; o[qq][1] = 0.f; }
+  for (int chunk = 0; chunk < nchunk; ++chunk) {
+    __syncthreads();
+    stage(chunk, 2 * H);
+    __syncthreads();
+    const int base = chunk * ATT_KC;
+    const int lim = min(ATT_KC, len - base);
+    int l = 0;
+    for (; l + 4 <= lim; l += 4) {
+      float4 pq[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int base = chunk * ATT_KC + j * 32;
-        if (base < len) {
-          const float pi = sc[chunk * 4 + j] * inv;
-          const int lim = min(32, len - base);
-          for (int l = 0; l < lim; ++l) {
-            const float pk = __shfl_sync(0xffffffffu, pi, l);
-            o0 = fmaf(pk, kv[j * 32 + l][lane], o0);
-            o1 = fmaf(pk, kv[j * 32 + l][lane + 32], o1);
-          }
+      for (int qq = 0; qq < 4; ++qq) pq[qq] = *reinterpret_cast<const float4*>(S + (qw + qq) * ld_s + base + l);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float v0 = kv[l + i][lane], v1 = kv[l + i][lane + 32];
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const float pk = i == 0 ? pq[qq].x : i == 1 ? pq[qq].y : i == 2 ? pq[qq].z : pq[qq].w;
+          o[qq][0] = fmaf(pk, v0, o[qq][0]);
+          o[qq][1] = fmaf(pk, v1, o[qq][1]);
         }
       }
     }
+    for (; l < lim; ++l) {
+      const float v0 = kv[l][lane], v1 = kv[l][lane + 32];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float pk = S[(qw + qq) * ld_s + base + l];
+        o[qq][0] = fmaf(pk, v0, o[qq][0]);
+        o[qq][1] = fmaf(pk, v1, o[qq][1]);
+      }
+    }
   }
-  if (valid) {
-    float* orow = ctx + (size_t)(seg.in_off + qi) * H + head * 64;
-    orow[lane] = o0;
-    orow[lane + 32] = o1;
+#pragma unroll
+  for (int qq = 0; qq < 4; ++qq) {
+    const int qi = q0 + qw + qq;
+    if (qi < len) {
+      float* orow = ctx + (size_t)(seg.in_off + qi) * H + head * 64;
+      orow[lane] = o[qq][0];
+      orow[lane + 32] = o[qq][1];
+    }
   }
 }
 
@@ -327,8 +357,19 @@ cudaError_t launch_fill_style(const float* style, int ld_style, int style_off, c
 cudaError_t launch_attention(const float* qkv, float* ctx, const Seg* segs, int nseg, int max_len, int heads, cudaStream_t s) {
   if (nseg <= 0 || max_len <= 0) return cudaSuccess;
   if (max_len > 32 * ATT_MAXK) return cudaErrorInvalidValue;
-  dim3 grid((max_len + ATT_QW - 1) / ATT_QW, heads, nseg);
-  attention_kernel<<<grid, ATT_QW * 32, 0, s>>>(qkv, ctx, segs, heads);
+  const int ld_s = (max_len + 3) & ~3;                      // float4 reads of the probabilities
+  const size_t smem = sizeof(float) * ((size_t)ATT_KC * ATT_LD + (size_t)ATT_QB * 64 + (size_t)ATT_QB * ld_s);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev] = true;
+  }
+  dim3 grid((max_len + ATT_QB - 1) / ATT_QB, heads, nseg);
+  attention_kernel<<<grid, 256, smem, s>>>(qkv, ctx, segs, heads, ld_s);
   return launched();
 }
 cudaError_t launch_duration(const float* logits, int ld, int nbins, const int* row2seg, const float* speeds, float* duration, int* pred_dur,
