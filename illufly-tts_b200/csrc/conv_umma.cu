@@ -766,46 +766,80 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   if (warp == NPW + 1) tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
 }
 
-// Split-fp16 operand images of a k=1 layer's input, one per (row tile, 64-channel chunk), laid out exactly like the kernel's
-// shared-memory slab ([hi | lo][8-channel plane][SR rows][8 x fp16]): the GEMM then bulk-copies them instead of converting
-// the same rows again for every Cout tile (the text-side GEMMs were producer bound: 18 Cout tiles re-converted each row tile).
-__global__ void __launch_bounds__(256) pack_split_kernel(const float* __restrict__ x, int ldx, int Cin, const Seg* __restrict__ segs,
-                                                         const Tile* __restrict__ tiles, int nsc, int SR, uint32_t slab_bytes,
-                                                         uint8_t* __restrict__ out) {
-  const Tile tile = tiles[blockIdx.x];
-  const Seg seg = segs[tile.seg];
+// Operand images of a layer's input, one per (row tile, K chunk), laid out exactly like the kernel's shared-memory slab
+// ([hi | lo][8-channel plane][SR rows][8 x 16 bit], fused prologue applied): a layer with several Cout tiles then bulk-copies
+// them instead of converting the same rows again for every Cout tile (the text-side GEMMs and the 1024-channel decoder convs
+// were producer bound: up to 18 Cout tiles re-converted each row tile).  Same arithmetic as the in-kernel producers.
+template <int PRO, int WFMT>
+__global__ void __launch_bounds__(256) pack_act_kernel(const ConvArgs p, int KS, int nsc, int SR, uint32_t slab_bytes, uint8_t* __restrict__ out) {
+  __shared__ float s_par[5][128];
+  const Tile tile = p.tiles[blockIdx.x];
+  const Seg seg = p.segs[tile.seg];
   const int sc = blockIdx.y;
+  const int planes = KS >> 3;
   uint8_t* blk = out + ((size_t)blockIdx.x * nsc + sc) * slab_bytes;
-  const size_t lo_off = (size_t)8 * SR * 16;
-  for (int idx = threadIdx.x; idx < 8 * SR; idx += blockDim.x) {
+  const size_t lo_off = (size_t)planes * SR * 16;
+  if (PRO >= PRO_ADAIN_LRELU) {
+    for (int cl = threadIdx.x; cl < KS; cl += blockDim.x) {
+      const int c = sc * KS + cl;
+      float mean = 0.f, a = 0.f, b = 0.f, al = 1.f;
+      if (c < p.Cin) {
+        const double* st = p.pstats + ((size_t)tile.seg * p.ld_pstats + c) * 2;
+        adain_coef(st, seg.in_len, p.gb[(size_t)tile.seg * p.ld_gb + c], p.gb[(size_t)tile.seg * p.ld_gb + p.beta_off + c], mean, a, b);
+        if (PRO == PRO_ADAIN_SNAKE) al = p.alpha[c];
+      }
+      const float Bf = fmaf(-mean, a, b);
+      const float kk = 0.5f / al;
+      s_par[0][cl] = a; s_par[1][cl] = (PRO == PRO_ADAIN_SNAKE) ? Bf + kk : Bf;
+      s_par[2][cl] = 2.f * al * a; s_par[3][cl] = 2.f * al * Bf; s_par[4][cl] = kk;
+    }
+    __syncthreads();
+  }
+  for (int idx = threadIdx.x; idx < planes * SR; idx += blockDim.x) {
     const int r = idx % SR, pln = idx / SR;
-    const int c0 = sc * 64 + pln * 8;
-    const int t = tile.t0 + r;
+    const int c0 = sc * KS + pln * 8;
+    const int traw = tile.t0 + r - p.pad;
+    const int tin = traw >> p.in_shr;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.f;
-    if (r < BM && t < seg.in_len && c0 < Cin) {
-      const float* src = x + (size_t)(seg.in_off + t) * ldx + c0;
-      if (c0 + 8 <= Cin && (ldx & 3) == 0) {
+    if (traw >= 0 && tin < seg.in_len && c0 < p.Cin) {
+      const float* src = p.x + (size_t)(seg.in_off + tin) * p.ldx + c0;
+      if (c0 + 8 <= p.Cin && (p.ldx & 3) == 0) {
         const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src + 4));
         v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
       } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) if (c0 + e < Cin) v[e] = __ldg(src + e);
+        for (int e = 0; e < 8; ++e) if (c0 + e < p.Cin) v[e] = __ldg(src + e);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float x = v[e];
+        const int cl = pln * 8 + e;
+        if (PRO == PRO_LRELU) x = fmaxf(x, x * p.slope);
+        else if (PRO == PRO_ADAIN_LRELU) { const float wv = fmaf(x, s_par[0][cl], s_par[1][cl]); x = fmaxf(wv, wv * p.slope); }
+        else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-s_par[4][cl], __cosf(fmaf(x, s_par[2][cl], s_par[3][cl])), fmaf(x, s_par[0][cl], s_par[1][cl]));
+        v[e] = (c0 + e < p.Cin) ? x : 0.f;
       }
     }
-    float hi[8], lo[8];
+    uint4 o;
+    if (WFMT == 2) {
+      float hi[8], lo[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xs = fminf(fmaxf(v[e] * SPLIT_SA, -65504.f), 65504.f);
-      hi[e] = __half2float(__float2half_rn(xs));
-      lo[e] = xs - hi[e];
-    }
-    uint4 oh, ol;
-    oh.x = pack_f16_nosat(hi[0], hi[1]); oh.y = pack_f16_nosat(hi[2], hi[3]); oh.z = pack_f16_nosat(hi[4], hi[5]); oh.w = pack_f16_nosat(hi[6], hi[7]);
-    ol.x = pack_f16_nosat(lo[0], lo[1]); ol.y = pack_f16_nosat(lo[2], lo[3]); ol.z = pack_f16_nosat(lo[4], lo[5]); ol.w = pack_f16_nosat(lo[6], lo[7]);
-    *reinterpret_cast<uint4*>(blk + (size_t)idx * 16) = oh;
-    *reinterpret_cast<uint4*>(blk + lo_off + (size_t)idx * 16) = ol;
+      for (int e = 0; e < 8; ++e) {
+        const float xs = fminf(fmaxf(v[e] * SPLIT_SA, -65504.f), 65504.f);
+        hi[e] = __half2float(__float2half_rn(xs));
+        lo[e] = xs - hi[e];
+      }
+      uint4 ol;
+      o.x = pack_f16_nosat(hi[0], hi[1]); o.y = pack_f16_nosat(hi[2], hi[3]); o.z = pack_f16_nosat(hi[4], hi[5]); o.w = pack_f16_nosat(hi[6], hi[7]);
+      ol.x = pack_f16_nosat(lo[0], lo[1]); ol.y = pack_f16_nosat(lo[2], lo[3]); ol.z = pack_f16_nosat(lo[4], lo[5]); ol.w = pack_f16_nosat(lo[6], lo[7]);
+      *reinterpret_cast<uint4*>(blk + lo_off + (size_t)idx * 16) = ol;
+    } else if (WFMT == 1) {
+      if (PRO >= PRO_ADAIN_LRELU) { o.x = pack_f16_nosat(v[0], v[1]); o.y = pack_f16_nosat(v[2], v[3]); o.z = pack_f16_nosat(v[4], v[5]); o.w = pack_f16_nosat(v[6], v[7]); }
+      else { o.x = pack_f16(v[0], v[1]); o.y = pack_f16(v[2], v[3]); o.z = pack_f16(v[4], v[5]); o.w = pack_f16(v[6], v[7]); }
+    } else { o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]); }
+    *reinterpret_cast<uint4*>(blk + (size_t)idx * 16) = o;
   }
 }
 
@@ -963,9 +997,14 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   u.prof = prof_on ? prof_buf : nullptr;
   u.xpack = nullptr;
   static const bool nopack = getenv("TTSB_UMMA_NOPACK") != nullptr;
-  if (a.xpack && a.wfmt == 2 && a.k == 1 && a.in_shr == 0 && a.pro == PRO_NONE && a.stride == 1 && a.pad == 0 && u.p.ntile_n > 1 && !nopack &&
-      (size_t)a.ntiles * u.p.nsc * u.p.slab_bytes <= a.xpack_bytes && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {
-    pack_split_kernel<<<dim3(a.ntiles, u.p.nsc), 256, 0, s>>>(a.x, a.ldx, a.Cin, a.segs, a.tiles, u.p.nsc, u.p.SR, u.p.slab_bytes, a.xpack);
+  // worth a pass of its own from three Cout tiles on (measured: at two the pack kernel costs what the producers save)
+  if (a.xpack && a.stride == 1 && u.p.ntile_n > 2 && !nopack && (size_t)a.ntiles * u.p.nsc * u.p.slab_bytes <= a.xpack_bytes &&
+      (reinterpret_cast<uintptr_t>(a.x) & 15) == 0) {
+    using PackFn = void (*)(const ConvArgs, int, int, int, uint32_t, uint8_t*);
+    static const PackFn ptable[4][3] = {
+        {pack_act_kernel<0, 0>, pack_act_kernel<0, 1>, pack_act_kernel<0, 2>}, {pack_act_kernel<1, 0>, pack_act_kernel<1, 1>, pack_act_kernel<1, 2>},
+        {pack_act_kernel<2, 0>, pack_act_kernel<2, 1>, pack_act_kernel<2, 2>}, {pack_act_kernel<3, 0>, pack_act_kernel<3, 1>, pack_act_kernel<3, 2>}};
+    ptable[a.pro][a.wfmt]<<<dim3(a.ntiles, u.p.nsc), 256, 0, s>>>(u.a, u.p.KS, u.p.nsc, u.p.SR, u.p.slab_bytes, a.xpack);
     cudaError_t e = launched();
     if (e != cudaSuccess) return e;
     u.xpack = a.xpack;

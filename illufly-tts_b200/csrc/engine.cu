@@ -518,15 +518,23 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   a.out_scale = c.out_scale; a.accumulate = c.accumulate; a.act = c.act; a.act_slope = c.act_slope;
   a.ostats = c.ostats; a.ld_ostats = c.w->Cout;
   a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
-  if (c.exact && a.k == 1 && r.e.precision != TTSB_PRECISION_FP32) {
-    // split-fp16 image of the input: 129-row slabs of 64 channels, hi + lo halves (conv_umma.cu: pack_split_kernel)
-    const size_t need = (size_t)t.ntiles * ((a.cin_pad + 63) / 64) * (2 * 8 * 129 * 16);
-    if (need > r.xpack_bytes) {
-      const size_t cap = need > ((size_t)24 << 20) ? need : ((size_t)24 << 20);
-      uint8_t* pnew = r.alloc<uint8_t>(cap);
-      if (pnew) { r.xpack = pnew; r.xpack_bytes = cap; }
+  if ((c.exact || c.tensor) && r.e.precision != TTSB_PRECISION_FP32 && a.stride == 1) {
+    // layers with several Cout tiles read pre-packed operand images (conv_umma.cu: pack_act_kernel); scratch sized for this call
+    const bool split = c.exact;
+    const int ks = split ? 64 : (a.cin_pad < 128 ? a.cin_pad : 128);
+    const int bn = split ? 128 : 256;
+    if (a.cout_pad > bn) {
+      const size_t sr = (size_t)((128 + (a.k - 1) * a.dil) | 1);
+      size_t slab = (size_t)(ks / 8) * sr * 16 * (split ? 2 : 1);
+      slab = (slab + 127) & ~(size_t)127;
+      const size_t need = (size_t)t.ntiles * (a.cin_pad / ks) * slab;
+      if (need > r.xpack_bytes && need <= ((size_t)512 << 20)) {
+        const size_t cap = need > ((size_t)32 << 20) ? need : ((size_t)32 << 20);
+        uint8_t* pnew = r.alloc<uint8_t>(cap);
+        if (pnew) { r.xpack = pnew; r.xpack_bytes = cap; }
+      }
+      a.xpack = r.xpack; a.xpack_bytes = r.xpack_bytes;
     }
-    a.xpack = r.xpack; a.xpack_bytes = r.xpack_bytes;
   }
   if (c.pro >= PRO_ADAIN_LRELU && (!c.pstats || !c.gb)) { set_error("internal: AdaIN prologue without statistics"); return TTSB_E_INVALID; }
   const double rows = (double)t.out_rows;
