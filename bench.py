@@ -251,7 +251,7 @@ def main():
         p = prof_acc[dom]
         ach = p["flops"] / (p["ms"] * 1e-3) / 1e12 if p["ms"] > 0 else 0.0
         traffic, traffic_note = None, None
-        tp = os.path.join(ROOT, "profiles", "r01g_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r01j_traffic.json")
         if dom == "conv_tensor" and os.path.exists(tp):
             with open(tp) as f:
                 tj = json.load(f)
