@@ -102,7 +102,8 @@ cudaError_t launch_conv1_s2(const float* x, float* y, int ldy, const float* w3, 
                             double* ostats, int ld_ostats, cudaStream_t s);
 cudaError_t launch_copy_cols(const float* src, int lds, float* dst, int ldd, int C, int rows, cudaStream_t s);
 cudaError_t launch_source_stft(const float* f0, const float* noise, const float* lin_w, const float* lin_b, float* har_src, float* har, int ld_har,
-                               float* scratch_phase, const Seg* segs, int nseg, int max_L, unsigned long long seed, cudaStream_t s);
+                               float* scratch_phase, const Seg* segs, int nseg, int max_L, unsigned long long seed, const unsigned long long* seg_seeds,
+                               cudaStream_t s);
 cudaError_t launch_up_add(const float* up, int ldu, int up_row_shift, int reflect, const float* xs, int ldxs, float* y, int ldy, int C,
                           const Seg* segs, int nseg, int max_out_len, double* ostats, int ld_ostats, cudaStream_t s);
 cudaError_t launch_istft(const float* cp, int ld, float* audio, const Seg* segs, int nseg, int max_frames, cudaStream_t s);

@@ -646,7 +646,7 @@ int run_resblock1(Run& r, const ResBlock1W& b, const float* x, const double* xst
 
 // kokoro Generator.forward: gen_in [sum L, 512] + f0 [sum L] + decoder-style gamma|beta rows -> audio [300 sum L]
 int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0, const float* gbD, int ld_gb, const float* noise, uint64_t seed,
-                  float* audio) {
+                  const std::vector<unsigned long long>* utt_seeds, float* audio) {
   Engine& e = r.e;
   const int nseg = spL.n();
   std::vector<int> lU0(nseg), lS0(nseg), lU1(nseg), lS1(nseg), lA(nseg);
@@ -656,7 +656,7 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   }
   Space spU0, spS0, spU1, spS1, spA;
   spU0.build(lU0); spS0.build(lS0); spU1.build(lU1); spS1.build(lS1); spA.build(lA);
-  RC(r.tables_begin((size_t)nseg * 20 * sizeof(Seg) + (size_t)(spS1.total / 128 + 8 * nseg + 64) * 5 * sizeof(Tile) + 4096));
+  RC(r.tables_begin((size_t)nseg * 20 * sizeof(Seg) + (size_t)(spS1.total / 128 + 8 * nseg + 64) * 5 * sizeof(Tile) + (size_t)nseg * 8 + 4096));
   // STFT-frame rows of the source features: every utterance starts at a multiple of 6 rows and is zero-padded to 60L+6 rows,
   // so that six consecutive frames can be viewed as one 144-float row (noise_convs[0] without a strided kernel)
   std::vector<int> offH(nseg), lenH(nseg);
@@ -680,6 +680,8 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   const SegTab tU1_S1 = r.make_tab(spU1, spS1, 6, 1, false);
   const SegTab tS1 = r.make_tab(spS1, spS1);
   const SegTab tS1_A = r.make_tab(spS1, spA, 1, 1, false);
+  // per-utterance seeds of the in-kernel SineGen noise (null: vocoder-only entry, noise keyed by position in the buffer)
+  const unsigned long long* seg_seeds = (utt_seeds && (int)utt_seeds->size() == nseg) ? r.push(*utt_seeds) : nullptr;
   RC(r.tables_upload());
 
   // ---- harmonic source + STFT (W10, W11) ----
@@ -688,7 +690,7 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   if (har) CK(cudaMemsetAsync(har, 0, sizeof(float) * (size_t)totH * 24, r.s));
   float* har_src = e.taps_on ? r.alloc<float>((size_t)spA.total) : nullptr;
   if (!phase || !har) return TTSB_E_NOMEM;
-  CK(launch_source_stft(f0, noise, e.src_lin_w, e.src_lin_b, har_src, har, 24, phase, tL_S1.segs, nseg, spL.maxlen, seed, r.s));
+  CK(launch_source_stft(f0, noise, e.src_lin_w, e.src_lin_b, har_src, har, 24, phase, tL_S1.segs, nseg, spL.maxlen, seed, seg_seeds, r.s));
   if (har_src) RC(r.tap("har_source", har_src, spA.total, 1, 1));
   RC(r.tap_ragged("har", har, 22, 24, offH, lenH));
 
@@ -794,6 +796,12 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   Space spFlat; spFlat.build({R});                      // Linear layers do not care about utterance boundaries: full 128-row tiles
   const SegTab tTf = r.make_tab(spFlat, spFlat);
   std::vector<int> h_ids(ids + token_offsets[0], ids + token_offsets[0] + R), h_pos(R), h_r2s(R);
+  e.utt_key.assign(B, 0);                               // FNV-1a of each utterance's token ids (engine_finish: noise seeds)
+  for (int b = 0; b < B; ++b) {
+    unsigned long long hsh = 0xCBF29CE484222325ull;
+    for (int i = token_offsets[b]; i < token_offsets[b + 1]; ++i) { hsh ^= (unsigned long long)(unsigned)ids[i]; hsh *= 0x100000001B3ull; }
+    e.utt_key[b] = hsh;
+  }
   std::vector<LstmSeg> ls(B), lsq(B);
   std::vector<float> h_speed(B), h_ref(ref_s, ref_s + (size_t)B * 256);
   for (int b = 0; b < B; ++b) {
@@ -1045,7 +1053,13 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
     d_audio = r.alloc<float>((size_t)RF * 600);
     if (!d_audio) return TTSB_E_NOMEM;
   }
-  RC(run_generator(r, spL, GIN, F0, gbD, ldD, d_noise, seed, d_audio));
+  // the noise an utterance draws depends on (seed, its own token ids), not on where it sits in the batch or on its neighbours
+  std::vector<unsigned long long> utt_seeds(e.utt_key.size());
+  for (size_t b = 0; b < utt_seeds.size(); ++b) {
+    unsigned long long z = (unsigned long long)seed + 0x9E3779B97F4A7C15ull * (e.utt_key[b] | 1ull);      // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; utt_seeds[b] = z ^ (z >> 31);
+  }
+  RC(run_generator(r, spL, GIN, F0, gbD, ldD, d_noise, seed, (int)utt_seeds.size() == spL.n() ? &utt_seeds : nullptr, d_audio));
   if (audio_mem != TTSB_MEM_DEVICE) CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * (size_t)RF * 600, cudaMemcpyDeviceToHost, r.s));
   CK(cudaEventRecord(e.ev_step1, r.s));
   if (audio_mem != TTSB_MEM_DEVICE || indices || e.taps_on || e.prof.on) {
@@ -1098,7 +1112,7 @@ int engine_vocoder(Engine& e, const float* x, const float* f0, const float* styl
     d_audio = r.alloc<float>(RL * 300);
     if (!d_audio) return TTSB_E_NOMEM;
   }
-  RC(run_generator(r, spL, dx, df0, gbD, e.style_dec.ldw, dnoise, seed, d_audio));
+  RC(run_generator(r, spL, dx, df0, gbD, e.style_dec.ldw, dnoise, seed, nullptr, d_audio));   // no token ids here: noise keyed by buffer position
   if (audio_mem != TTSB_MEM_DEVICE) CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * RL * 300, cudaMemcpyDeviceToHost, r.s));
   CK(cudaEventRecord(e.ev_step1, r.s));
   if (audio_mem != TTSB_MEM_DEVICE || e.taps_on || e.prof.on) {

@@ -115,6 +115,7 @@ struct Engine {
   Profiler prof;
   int precision = 0;
   bool taps_on = false;
+  std::vector<unsigned long long> utt_key;   // per utterance of the step in flight: hash of its token ids (begin -> finish)
   bool finalized = false;
   std::map<std::string, HostTensor> host;       // raw checkpoint tensors until finalize()
   std::vector<void*> dev_allocs;                // weights

@@ -242,13 +242,18 @@ constexpr int SF = 64;
 constexpr int SS = 5 * (SF - 1) + 20;   // 335 samples per tile
 __global__ void __launch_bounds__(128) source_stft_kernel(const float* __restrict__ f0, const float* __restrict__ noise, const float* __restrict__ lw,
                                                           const float* __restrict__ lb, float* __restrict__ har_src, float* __restrict__ har, int ld_har,
-                                                          const float* __restrict__ phase, const Seg* __restrict__ segs, unsigned long long seed) {
+                                                          const float* __restrict__ phase, const Seg* __restrict__ segs, unsigned long long seed,
+                                                          const unsigned long long* __restrict__ seg_seeds) {
   __shared__ float xs[SS];
   const Seg seg = segs[blockIdx.y];      // in: L rows of f0 ; out: 60L+1 har rows
   const int fr0 = blockIdx.x * SF;
   if (fr0 >= seg.out_len) return;
   const int L = seg.in_len, N = 300 * L;
   const size_t samp_off = (size_t)seg.in_off * 300;   // utterance's first audio-rate sample
+  // in-kernel SineGen noise: with a seed table the stream is keyed by (utterance seed, sample index WITHIN the utterance), so an
+  // utterance draws the same noise wherever it sits in a batch; without one (vocoder-only entry) by (seed, position in the buffer)
+  const unsigned long long nz_seed = seg_seeds ? seg_seeds[blockIdx.y] : seed;
+  const size_t nz_base = seg_seeds ? 0 : samp_off;
   for (int i = threadIdx.x; i < SS; i += blockDim.x) {
     int j = 5 * fr0 + i - 10;            // sample index before reflection
     float v = 0.f;
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(128) source_stft_kernel(const float* __restric
     if (j < 0) j = -j;
     if (j >= N) j = 2 * (N - 1) - j;
     if (j >= 0 && j < N) {
-      v = har_sample(j, f0 + seg.in_off, phase + (size_t)seg.in_off * 9, L, noise ? noise + (samp_off + j) * 9 : nullptr, lw, lb[0], seed, samp_off + j);
+      v = har_sample(j, f0 + seg.in_off, phase + (size_t)seg.in_off * 9, L, noise ? noise + (samp_off + j) * 9 : nullptr, lw, lb[0], nz_seed, nz_base + j);
       if (inside && har_src && i >= 10 && (i < 10 + 5 * SF || 5 * fr0 + i - 10 >= N - 10)) har_src[samp_off + j] = v;
     }
     xs[i] = v;
@@ -442,7 +447,8 @@ cudaError_t launch_copy_cols(const float* src, int lds, float* dst, int ldd, int
   return launched();
 }
 cudaError_t launch_source_stft(const float* f0, const float* noise, const float* lin_w, const float* lin_b, float* har_src, float* har, int ld_har,
-                               float* scratch_phase, const Seg* segs, int nseg, int max_L, unsigned long long seed, cudaStream_t s) {
+                               float* scratch_phase, const Seg* segs, int nseg, int max_L, unsigned long long seed, const unsigned long long* seg_seeds,
+                               cudaStream_t s) {
   if (nseg <= 0 || max_L <= 0) return cudaSuccess;
   cudaError_t e = ensure_tables();
   if (e != cudaSuccess) return e;
@@ -451,7 +457,7 @@ cudaError_t launch_source_stft(const float* f0, const float* noise, const float*
   if ((e = launched()) != cudaSuccess) return e;
   const int max_frames = 60 * max_L + 1;
   dim3 grid((max_frames + SF - 1) / SF, nseg);
-  source_stft_kernel<<<grid, 128, 0, s>>>(f0, noise, lin_w, lin_b, har_src, har, ld_har, phase, segs, seed);
+  source_stft_kernel<<<grid, 128, 0, s>>>(f0, noise, lin_w, lin_b, har_src, har, ld_har, phase, segs, seed, seg_seeds);
   return launched();
 }
 cudaError_t launch_up_add(const float* up, int ldu, int up_row_shift, int reflect, const float* xs, int ldxs, float* y, int ldy, int C,

@@ -119,7 +119,10 @@ TTSB_API int ttsb_synthesize_begin(ttsb_engine* e, const int32_t* ids, const int
 
 /* finish(): kmodel.py:120-143 — length regulation, F0Ntrain, text_encoder, decoder + iSTFTNet generator.
  *   noise       fp32 [600*sum F, 9] N(0,1) samples for SineGen (injected for parity), in `noise_mem`; or NULL:
- *               the engine draws them in-kernel (Philox) from `seed`
+ *               the engine draws them in-kernel (Philox).  The stream of an utterance is keyed by (`seed`, a hash of that
+ *               utterance's own token ids, sample index within the utterance): the same utterance with the same `seed` draws
+ *               the same noise wherever it sits in a batch and whatever else is in it; another `seed` gives another draw.
+ *               (ttsb_vocoder has no token ids: there the stream is keyed by `seed` and the position in the batch's buffer.)
  *   indices     host int32 [sum F] or NULL — the alignment index map (token index of each frame; kmodel.py:116-119)
  *   audio       fp32 [600*sum F] in `audio_mem` (TTSB_MEM_HOST: the engine does the D2H copy; TTSB_MEM_DEVICE:
  *               written in place, valid when `stream` has drained)

@@ -185,6 +185,61 @@ def test_batchkmodel_surface(checkpoint, oracle):
     assert len(short) == 1 and short[0].shape == (24000,)
 
 
+def test_service_is_a_pure_scheduler_and_batch_invariant(checkpoint, oracle):
+    """SURVEY 8(f) row 1 (illufly-tts_b200/service.py) on the real engine, f16, per-utterance semantics (padded_lstm=False):
+    (1) what a task receives is bit-identical to replaying the engine call it rode in (the service adds nothing to the numerics
+        and the engine is reproducible run to run; measured 96 of 96 waveforms identical, tests/bench_service.py probe);
+    (2) a request synthesised ALONE gives the same number of samples (= the same integer durations, also against the oracle) and
+        the same waveform as inside a service batch with other users' requests: measured SNR 333-336 dB, bar 100 dB.  This holds
+        for the in-kernel SineGen noise too, which is keyed by (seed, the utterance's own token ids, sample index within the
+        utterance) - with the noise keyed by buffer position it was -0.7 dB for every request not at batch position 0;
+    (3) a user's tasks complete in sequence order."""
+    import asyncio
+
+    from illufly_tts_b200.service import voice_row
+    model = pkg.BatchKModel(config=synthetic_config(), model=checkpoint, precision=pkg.PRECISION_FP16, strict=True, padded_lstm=False).to("cuda:0")
+    voices = {"a": synthetic_voice_pack(1), "b": synthetic_voice_pack(2)}
+    calls = []
+
+    class Recorder:
+        def forward_batch(self, phonemes, ref_s, speeds=None):
+            out = model.forward_batch(phonemes, ref_s, speeds)
+            calls.append((list(phonemes), ref_s.clone(), list(speeds), [a.clone() for a in out]))
+            return out
+    g = torch.Generator().manual_seed(21)
+    lens = [9, 64, 33, 120, 17, 80, 45, 5, 101, 60, 28, 72, 14, 90, 38, 55]
+    ids = [random_ids(g, n) for n in lens]
+    reqs = [(ids_to_phonemes(x), "ab"[k % 2], [1.0, 0.85, 1.2][k % 3], f"user{k % 4}") for k, x in enumerate(ids)]
+
+    async def main():
+        svc = pkg.TTSServiceManager(Recorder(), voices, token_budget=400)
+        tids = [await svc.submit_task(ph, v, sp, user_id=u, sequence_id=float(k)) for k, (ph, v, sp, u) in enumerate(reqs)]
+        await svc.start()
+        for t in tids:
+            async for _ in svc.stream_result(t):
+                pass
+        await svc.stop()
+        return svc, tids
+    svc, tids = asyncio.run(main())
+    assert all(svc.tasks[t].status == pkg.TaskStatus.COMPLETED for t in tids) and len(calls) >= 3
+    assert all(sum(len(p) + 2 for p in c[0]) <= 400 for c in calls)
+    got = {reqs[k][0]: svc.tasks[t].audio_chunks[0] for k, t in enumerate(tids)}
+    for ph, ref, sp, out in calls:                                   # (1)
+        again = model.forward_batch(ph, ref, sp)
+        for p, a, b in zip(ph, out, again):
+            assert torch.equal(a, b), "engine call not reproducible"
+            assert torch.equal(got[p], a), "the task did not receive what the engine returned"
+    for k in (1, 3, 8, 12):                                          # (2)
+        ph, v, sp, _ = reqs[k]
+        solo = model.forward_batch([ph], voice_row(voices[v], len(ph)).unsqueeze(0), [sp])[0]
+        o = oracle.forward_batch([ids[k]], voice_row(voices[v], len(ph)), [sp], stop_after_durations=True)
+        assert solo.numel() == got[ph].numel() == 600 * int(o.pred_dur[0].sum())
+        assert snr_db(solo.cpu(), got[ph].cpu()) > 100.0
+    for u in range(4):                                               # (3)
+        done = [svc.tasks[t].completed_at for k, t in enumerate(tids) if k % 4 == u]
+        assert done == sorted(done)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # single kernels
 # ---------------------------------------------------------------------------------------------------------

@@ -1,0 +1,202 @@
+"""Host logic of the continuous batcher (illufly-tts_b200/service.py) against the properties the reference's service encodes
+(/root/reference/src/illufly_tts/core/service.py): task states and status dict, cancel only while pending, per-user order,
+fairness across users; plus what the new policy adds: token budget, several chunks per task, failure isolation.
+CPU only: the model is a recording stand-in with the ``forward_batch`` signature of BatchKModel."""
+import asyncio
+import threading
+import time
+
+import pytest
+import torch
+
+import illufly_tts_b200 as pkg
+from illufly_tts_b200.service import voice_row
+
+VOICES = {"v1": torch.arange(510 * 256, dtype=torch.float32).reshape(510, 1, 256), "v2": torch.ones(510, 1, 256)}
+STATUS_KEYS = {"task_id", "status", "created_at", "started_at", "completed_at", "text", "voice_id", "user_id", "chunks_completed"}   # service.py:150-160
+
+
+class FakeModel:
+    """forward_batch(list[str], ref_s [B,1,256], speeds) -> list of 1-D tensors; remembers every call."""
+
+    def __init__(self, delay=0.0, poison=None, gate: threading.Event = None):
+        self.calls, self.delay, self.poison, self.gate = [], delay, poison, gate
+
+    def forward_batch(self, phonemes, ref_s, speeds=None):
+        assert ref_s.shape == (len(phonemes), 1, 256)
+        self.calls.append(list(phonemes))
+        if self.gate is not None:
+            self.gate.wait(5.0)
+        if self.delay:
+            time.sleep(self.delay)
+        if self.poison is not None and any(self.poison in p for p in phonemes):
+            raise RuntimeError("poisoned batch")
+        return [torch.full((600 * len(p),), float(len(p)) + float(ref_s[i, 0, 0]) * 1e-6) for i, p in enumerate(phonemes)]
+
+
+def run(coro):
+    return asyncio.run(coro)
+
+
+async def drain(svc, ids, timeout=10.0):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        st = [svc.tasks[i].status for i in ids]
+        if all(s in (pkg.TaskStatus.COMPLETED, pkg.TaskStatus.FAILED, pkg.TaskStatus.CANCELED) for s in st):
+            return
+        await asyncio.sleep(0.002)
+    raise AssertionError("tasks did not finish")
+
+
+def test_lifecycle_and_status_dict():
+    async def main():
+        svc = pkg.TTSServiceManager(FakeModel(), VOICES)
+        await svc.start()
+        tid = await svc.submit_task("abcdefgh", "v1", 1.1, user_id="u", debug_id="d", sequence_id=3.0)
+        st = await svc.get_task_status(tid)
+        assert set(st) == STATUS_KEYS and st["status"] in ("pending", "processing", "completed") and st["text"] == "abcdefgh"
+        await drain(svc, [tid])
+        st = await svc.get_task_status(tid)
+        assert st["status"] == "completed" and st["chunks_completed"] == 1 and st["started_at"] <= st["completed_at"]
+        chunks = [c async for c in svc.stream_result(tid)]
+        assert len(chunks) == 1 and chunks[0].numel() == 600 * 8
+        assert await svc.get_task_status("nope") is None
+        assert [s["task_id"] for s in await svc.get_user_tasks("u")] == [tid]
+        await svc.stop()
+    run(main())
+
+
+def test_unknown_voice_is_born_failed_and_stream_raises():
+    async def main():
+        svc = pkg.TTSServiceManager(FakeModel(), VOICES)
+        await svc.start()
+        tid = await svc.submit_task("abcdef", "nobody")
+        st = await svc.get_task_status(tid)
+        assert st["status"] == "failed" and st["completed_at"] is not None                 # service.py:88-101
+        with pytest.raises(ValueError):
+            [c async for c in svc.stream_result(tid)]
+        with pytest.raises(ValueError):
+            [c async for c in svc.stream_result("nope")]
+        await svc.stop()
+    run(main())
+
+
+def test_cancel_only_while_pending():
+    async def main():
+        gate = threading.Event()
+        model = FakeModel(gate=gate)
+        svc = pkg.TTSServiceManager(model, VOICES, token_budget=12)
+        a = await svc.submit_task("aaaaaaaaaa", "v1", user_id="u")        # 12 tokens: fills the first batch alone
+        b = await svc.submit_task("bbbbbbbbbb", "v1", user_id="u")
+        await svc.start()
+        while not model.calls:
+            await asyncio.sleep(0.001)
+        assert svc.tasks[a].status == pkg.TaskStatus.PROCESSING
+        assert not await svc.cancel_task(a)                                # service.py:133-135: already started
+        assert await svc.cancel_task(b) and not await svc.cancel_task(b) and not await svc.cancel_task("nope")
+        gate.set()
+        await drain(svc, [a, b])
+        assert svc.tasks[a].status == pkg.TaskStatus.COMPLETED and svc.tasks[b].status == pkg.TaskStatus.CANCELED
+        assert model.calls == [["aaaaaaaaaa"]]                             # the canceled task never reached the engine
+        with pytest.raises(ValueError):
+            [c async for c in svc.stream_result(b)]
+        await svc.stop()
+    run(main())
+
+
+def test_budget_fairness_and_per_user_order():
+    async def main():
+        model = FakeModel(delay=0.002)
+        svc = pkg.TTSServiceManager(model, VOICES, token_budget=50, max_batch_items=64)
+        heavy = [await svc.submit_task("h" * 8 + f"{i:02d}", "v1", user_id="heavy", sequence_id=float(i)) for i in range(20)]    # 12 tokens each
+        light = await svc.submit_task("l" * 10, "v2", user_id="light", sequence_id=100.0)
+        await svc.start()
+        await drain(svc, heavy + [light])
+        assert any("l" * 10 in call for call in model.calls[:1]), "the light user's only task must ride in the first batch"
+        for call in model.calls:
+            assert sum(len(p) + 2 for p in call) <= 50
+        assert max(len(c) for c in model.calls) == 4 and len(model.calls) < 21     # batches are filled, not one task per user
+        done = [svc.tasks[t].completed_at for t in heavy]
+        assert done == sorted(done), "a user's tasks complete in sequence order"
+        order = [p for call in model.calls for p in call if p.startswith("h")]
+        assert order == sorted(order), "and reach the engine in sequence order"
+        await svc.stop()
+    run(main())
+
+
+def test_later_task_never_overtakes_one_that_does_not_fit():
+    svc = pkg.TTSServiceManager(FakeModel(), VOICES, token_budget=30)
+
+    async def main():
+        await svc.submit_task("a" * 10, "v1", user_id="u", sequence_id=1.0)      # 12
+        await svc.submit_task("b" * 25, "v1", user_id="u", sequence_id=2.0)      # 27: does not fit after the first
+        await svc.submit_task("c" * 4, "v1", user_id="u", sequence_id=3.0)       # 6: would fit, but must wait for b
+        await svc.submit_task("d" * 4, "v1", user_id="w", sequence_id=4.0)
+    run(main())
+    assert [t.text[0] for t in svc.select_batch()] == ["a", "d"]
+
+
+def test_oversize_task_gets_its_own_batch_and_chunks_stay_together():
+    async def main():
+        model = FakeModel()
+        svc = pkg.TTSServiceManager(model, VOICES, token_budget=20, g2p=lambda text: text.split("|"))
+        big = await svc.submit_task("x" * 30 + "|" + "y" * 30 + "|" + "z" * 5, "v1", user_id="a")
+        small = await svc.submit_task("s" * 6, "v1", user_id="b")
+        await svc.start()
+        await drain(svc, [big, small])
+        assert model.calls[0] == ["x" * 30, "y" * 30, "z" * 5] and model.calls[1] == ["s" * 6]
+        chunks = [c async for c in svc.stream_result(big)]
+        assert [c.numel() for c in chunks] == [600 * 30, 600 * 30, 600 * 5]          # chunk order of the text
+        assert (await svc.get_task_status(big))["chunks_completed"] == 3
+        await svc.stop()
+    run(main())
+
+
+def test_voice_row_follows_length_like_the_pipeline():
+    pack = VOICES["v1"]
+    assert torch.equal(voice_row(pack, 1), pack[0]) and torch.equal(voice_row(pack, 75), pack[74]) and torch.equal(voice_row(pack, 9999), pack[509])
+
+    async def main():
+        seen = []
+
+        class M(FakeModel):
+            def forward_batch(self, phonemes, ref_s, speeds=None):
+                seen.append((list(phonemes), ref_s.clone(), list(speeds)))
+                return super().forward_batch(phonemes, ref_s, speeds)
+        svc = pkg.TTSServiceManager(M(), VOICES)
+        t = await svc.submit_task("q" * 7, "v1", 0.9)
+        await svc.start()
+        await drain(svc, [t])
+        ph, ref, sp = seen[0]
+        assert torch.equal(ref[0], pack[6]) and sp == [0.9]
+        await svc.stop()
+    run(main())
+
+
+def test_failure_is_isolated_by_bisection():
+    async def main():
+        model = FakeModel(poison="BAD")
+        svc = pkg.TTSServiceManager(model, VOICES, token_budget=1000)
+        ids = [await svc.submit_task(("BAD" if i == 5 else "ok") + "p" * 6 + str(i), "v1", user_id=f"u{i}") for i in range(9)]
+        await svc.start()
+        await drain(svc, ids)
+        st = [svc.tasks[i].status for i in ids]
+        assert st[5] == pkg.TaskStatus.FAILED and "poisoned" in svc.tasks[ids[5]].error
+        assert all(s == pkg.TaskStatus.COMPLETED for k, s in enumerate(st) if k != 5), "one bad request must not fail its neighbours"
+        assert len(model.calls[0]) == 9 and len(model.calls) <= 1 + 2 * 4             # one full call, then a bisection
+        await svc.stop()
+    run(main())
+
+
+def test_reference_policy_is_one_task_per_user_at_most_four():
+    async def main():
+        model = FakeModel()
+        svc = pkg.ReferencePolicyManager(model, VOICES, batch_size=4)
+        ids = [await svc.submit_task("p" * 6 + f"{u}{i}", "v1", user_id=f"u{u}", sequence_id=float(i)) for u in range(6) for i in range(3)]
+        single = [await svc.submit_task("s" * 6 + str(i), "v1", user_id="solo", sequence_id=10.0 + i) for i in range(3)]
+        await svc.start()
+        await drain(svc, ids + single)
+        for call in model.calls:
+            assert len(call) <= 4 and len({p[6] for p in call if p.startswith("p")}) == len([p for p in call if p.startswith("p")])
+        await svc.stop()
+    run(main())
