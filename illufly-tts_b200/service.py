@@ -76,9 +76,12 @@ def voice_row(pack: torch.Tensor, n_symbols: int) -> torch.Tensor:
 
 class TTSServiceManager:
     def __init__(self, model, voices: Mapping[str, torch.Tensor], *, token_budget: int = 3200, max_batch_items: int = 64,
-                 max_wait_time: float = 0.0, g2p: Optional[Callable[[str], Sequence[str]]] = None):
+                 max_wait_time: float = 0.0, g2p: Optional[Callable[[str], Sequence[str]]] = None,
+                 load_voice: Optional[Callable[[str], torch.Tensor]] = None):
         """``model.forward_batch(list[str], ref_s [B,1,256], speeds) -> list[Tensor]`` is ``BatchKModel`` (or a stand-in in
-        tests).  ``voices``: voice id -> pack [510,1,256].  ``token_budget``: tokens (phonemes + BOS/EOS) per engine call;
+        tests).  ``voices``: voice id -> pack [510,1,256]; ``load_voice(voice_id)`` (the reference's ``pipeline.load_voice``,
+        pipeline.py:78-109, which fills its ``voices`` dict on demand and raises ValueError for an unknown id) is called for an id
+        that is not in ``voices`` yet, as the reference's ``submit_task`` does (:88-101).  ``token_budget``: tokens (phonemes + BOS/EOS) per engine call;
         3200 is the size of BASELINE configs[1] (32 utterances of 60-90 symbols, ~5 GB of workspace).  ``max_wait_time``:
         how long a batch smaller than the budget waits for more arrivals (0 = never; the reference has the parameter,
         :53, and never reads it)."""
@@ -90,6 +93,7 @@ class TTSServiceManager:
         self.max_batch_items = max_batch_items
         self.max_wait_time = max_wait_time
         self.g2p = g2p or (lambda text: [text])
+        self.load_voice = load_voice
         self.tasks: Dict[str, TTSTask] = {}
         self.processing_task: Optional[asyncio.Task] = None
         self._wake: Optional[asyncio.Event] = None
@@ -98,28 +102,38 @@ class TTSServiceManager:
     # ---- the reference's public surface -------------------------------------------------------------------
     async def submit_task(self, text: str, voice_id: str, speed: float = 1.0, user_id: Optional[str] = None,
                           debug_id: Optional[str] = None, sequence_id: Optional[float] = None) -> str:
+        # Everything that can suspend or fail happens BEFORE the task is registered: the batch loop runs whenever this coroutine
+        # awaits, and must never see a half-built PENDING task (the reference, too, loads the voice first: service.py:88-107).
+        problem = None
+        if voice_id not in self.voices and self.load_voice is not None:
+            try:                                            # service.py:91: load on demand, off the event loop
+                pack = await asyncio.to_thread(self.load_voice, voice_id)
+                if voice_id not in self.voices:
+                    self.voices[voice_id] = pack            # pipeline.load_voice stores it itself when `voices` is its dict
+            except Exception as exc:
+                problem = f"voice {voice_id!r} could not be loaded: {exc}"
+        if problem is None and voice_id not in self.voices:  # service.py:88-101: a task that is born FAILED
+            problem = f"voice {voice_id!r} is not loaded"
+        chunks: List[str] = []
+        if problem is None:
+            try:
+                chunks = [c for c in self.g2p(text) if c]
+                if not chunks:
+                    problem = "empty text"
+            except Exception as exc:
+                problem = f"g2p failed: {exc}"
         task_id = str(uuid.uuid4())
         task = TTSTask(task_id, text, voice_id, speed, user_id)
         task.debug_id = debug_id
         if sequence_id is not None:
             task.sequence_id = sequence_id
-        self.tasks[task_id] = task
-        problem = None
-        if voice_id not in self.voices:                    # service.py:88-101: a task that is born FAILED
-            problem = f"voice {voice_id!r} is not loaded"
-        else:
-            try:
-                task.chunks = [c for c in self.g2p(text) if c]
-                if not task.chunks:
-                    problem = "empty text"
-            except Exception as exc:
-                problem = f"g2p failed: {exc}"
+        task.chunks = chunks
         if problem:
             task.status = TaskStatus.FAILED
             task.error = problem
             task.completed_at = time.time()
-            return task_id
-        if self._wake is not None:
+        self.tasks[task_id] = task                          # no await between here and the return
+        if not problem and self._wake is not None:
             self._wake.set()
         return task_id
 
@@ -176,7 +190,7 @@ class TTSServiceManager:
         (order within a user); a task larger than the budget gets a batch of its own."""
         per_user: Dict[str, List[TTSTask]] = {}
         for t in self.tasks.values():
-            if t.status == TaskStatus.PENDING:
+            if t.status == TaskStatus.PENDING and t.chunks:
                 per_user.setdefault(t.user_id or "anonymous", []).append(t)
         for lst in per_user.values():
             lst.sort(key=lambda t: (t.sequence_id, t.created_at))
@@ -222,8 +236,8 @@ class TTSServiceManager:
             self.batch_log.append({"utterances": len(units), "tokens": sum(len(u[0]) + 2 for u in units), "seconds": time.perf_counter() - t0})
             return out
         except Exception as exc:
-            if len(units) == 1:
-                return [exc]
+            if len(units) <= 1:                             # also terminates on an empty list
+                return [exc] * len(units)
             mid = len(units) // 2
             return self._run_isolating(units[:mid]) + self._run_isolating(units[mid:])
 
@@ -242,20 +256,32 @@ class TTSServiceManager:
                 batch = self.select_batch()
             now = time.time()
             units: List[tuple] = []
-            for t in batch:
+            live: List[TTSTask] = []
+            for t in batch:                                 # a task whose inputs cannot be assembled fails alone
                 t.status = TaskStatus.PROCESSING
                 t.started_at = now
-                pack = self.voices[t.voice_id]
-                units += [(c, voice_row(pack, len(c)), float(t.speed)) for c in t.chunks]
-            results = await asyncio.to_thread(self._run_isolating, units)
+                try:
+                    pack = self.voices[t.voice_id]
+                    mine = [(c, voice_row(pack, len(c)), float(t.speed)) for c in t.chunks]
+                except Exception as exc:
+                    t.status, t.error, t.completed_at = TaskStatus.FAILED, f"could not assemble the request: {exc!r}", time.time()
+                    continue
+                units += mine
+                live.append(t)
+            if not live:
+                continue
+            try:
+                results = await asyncio.to_thread(self._run_isolating, units)
+            except Exception as exc:                        # nothing may kill the loop: every later task would hang (service.py:336-343)
+                results = [exc] * len(units)
             pos = 0
-            for t in batch:                                 # in selection order: sequence order within every user
+            for t in live:                                  # in selection order: sequence order within every user
                 mine = results[pos:pos + len(t.chunks)]
                 pos += len(t.chunks)
                 bad = next((r for r in mine if isinstance(r, Exception)), None)
-                if bad is not None:
+                if bad is not None or len(mine) != len(t.chunks):
                     t.status = TaskStatus.FAILED
-                    t.error = str(bad)
+                    t.error = str(bad) if bad is not None else "the engine returned too few waveforms"
                 else:
                     t.audio_chunks.extend(mine)
                     t.status = TaskStatus.COMPLETED

@@ -200,3 +200,88 @@ def test_reference_policy_is_one_task_per_user_at_most_four():
             assert len(call) <= 4 and len({p[6] for p in call if p.startswith("p")}) == len([p for p in call if p.startswith("p")])
         await svc.stop()
     run(main())
+
+
+def test_voices_are_loaded_on_demand_like_the_reference():
+    """pipeline.voices starts empty and pipeline.load_voice fills it (pipeline.py:78-109); submit_task loads before it judges
+    (service.py:88-101): a voice that is merely not loaded yet must not fail the task, an unknown one must."""
+    async def main():
+        store, loads = {}, []
+
+        def load_voice(vid):
+            loads.append(vid)
+            if vid not in VOICES:
+                raise ValueError(f"no such voice {vid}")
+            store[vid] = VOICES[vid]                       # the reference's loader stores into its own dict
+            return VOICES[vid]
+        svc = pkg.TTSServiceManager(FakeModel(), store, load_voice=load_voice)
+        await svc.start()
+        a = await svc.submit_task("abcdefg", "v1")
+        b = await svc.submit_task("abcdefg", "v1")
+        c = await svc.submit_task("abcdefg", "ghost")
+        await drain(svc, [a, b, c])
+        assert svc.tasks[a].status == svc.tasks[b].status == pkg.TaskStatus.COMPLETED
+        assert svc.tasks[c].status == pkg.TaskStatus.FAILED and "ghost" in svc.tasks[c].error
+        assert loads == ["v1", "ghost"], "a loaded voice is not loaded again"
+        await svc.stop()
+    run(main())
+
+
+def test_slow_voice_load_never_exposes_a_half_built_task():
+    """submit_task suspends while the voice loads; the batch loop runs meanwhile and must not pick the task up before its
+    chunks exist (regression: a PENDING task without chunks gave the engine an empty batch)."""
+    async def main():
+        store = {"v2": VOICES["v2"]}
+
+        def slow_load(vid):
+            time.sleep(0.05)
+            store[vid] = VOICES[vid]
+            return VOICES[vid]
+        model = FakeModel()
+        svc = pkg.TTSServiceManager(model, store, load_voice=slow_load)
+        await svc.start()
+        slow = asyncio.create_task(svc.submit_task("slowslow", "v1", user_id="a"))
+        await asyncio.sleep(0.005)
+        fast = await svc.submit_task("fastfast", "v2", user_id="b")        # wakes the loop while the other submit is suspended
+        await drain(svc, [fast])
+        assert all(len(c) > 0 for c in model.calls)
+        tid = await slow
+        await drain(svc, [tid])
+        assert svc.tasks[tid].status == pkg.TaskStatus.COMPLETED and all(len(c) > 0 for c in model.calls)
+        assert [c.numel() for c in svc.tasks[tid].audio_chunks] == [600 * 8], "the slow task must receive its audio"
+        assert ["slowslow"] in model.calls
+        await svc.stop()
+    run(main())
+
+
+def test_bisection_terminates_on_degenerate_input():
+    svc = pkg.TTSServiceManager(FakeModel(poison="x"), VOICES)
+    assert svc._run_isolating([]) == []
+    out = svc._run_isolating([("x" * 6, VOICES["v1"][0], 1.0)])
+    assert len(out) == 1 and isinstance(out[0], Exception)
+
+
+def test_a_task_that_cannot_be_assembled_fails_alone_and_the_loop_survives():
+    """the loop must outlive anything a single request can do to it (the reference guards its batch body, service.py:336-343)"""
+    async def main():
+        store = dict(VOICES)
+        gate = threading.Event()
+        svc = pkg.TTSServiceManager(FakeModel(gate=gate), store, token_budget=12)
+        first = await svc.submit_task("a" * 10, "v1", user_id="u1")          # fills batch 1 alone and blocks on the gate
+        await svc.start()
+        while svc.tasks[first].status != pkg.TaskStatus.PROCESSING:
+            await asyncio.sleep(0.001)
+        doomed = await svc.submit_task("b" * 10, "v2", user_id="u2")
+        okay = await svc.submit_task("c" * 10, "v1", user_id="u3", speed="not a number")
+        fine = await svc.submit_task("d" * 10, "v1", user_id="u4")
+        del store["v2"]                                                       # the voice disappears before its batch is built
+        gate.set()
+        await drain(svc, [first, doomed, okay, fine])
+        assert svc.tasks[doomed].status == pkg.TaskStatus.FAILED and "assemble" in svc.tasks[doomed].error
+        assert svc.tasks[okay].status == pkg.TaskStatus.FAILED
+        assert svc.tasks[first].status == svc.tasks[fine].status == pkg.TaskStatus.COMPLETED
+        later = await svc.submit_task("e" * 10, "v1", user_id="u5")          # the loop is still alive
+        await drain(svc, [later])
+        assert svc.tasks[later].status == pkg.TaskStatus.COMPLETED and not svc.processing_task.done()
+        await svc.stop()
+    run(main())
