@@ -6,6 +6,8 @@ all arithmetic happens in libttsb200.so.  Nothing in this module computes on the
 from __future__ import annotations
 
 import ctypes as C
+import functools
+import threading
 from dataclasses import dataclass, field
 from typing import Dict, List, Mapping, Optional, Sequence
 
@@ -37,6 +39,17 @@ def _ptr(a) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
 
 
+def _serialised(method):
+    """One engine = one CUDA stream + one workspace, and a synthesis is a begin -> finish PAIR with state in between: callers
+    on different threads (the reference reaches its model through ``asyncio.to_thread`` from several places) take turns.
+    Without this, a second thread's begin() would reset the workspace under the first thread's finish(): wrong audio, silently."""
+    @functools.wraps(method)
+    def locked(self, *a, **kw):
+        with self._lock:
+            return method(self, *a, **kw)
+    return locked
+
+
 class Engine:
     """One engine = one GPU.  Mirrors what kokoro's ``KModel.__init__`` + ``.to(device)`` do for the reference:
     take the checkpoint ``{bert, bert_encoder, predictor, decoder, text_encoder}`` of state dicts (``module.``
@@ -44,6 +57,7 @@ class Engine:
 
     def __init__(self, checkpoint: Mapping[str, Mapping[str, torch.Tensor]], device: int | str | torch.device = 0,
                  precision: int = PRECISION_FP32):
+        self._lock = threading.RLock()
         self._lib = _lib.load()
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         if dev.type != "cuda":
@@ -83,6 +97,7 @@ class Engine:
         except Exception:
             pass
 
+    @_serialised
     def set_precision(self, precision: int):
         _lib.check(self._lib.ttsb_engine_set_precision(self._h, int(precision)))
 
@@ -90,6 +105,7 @@ class Engine:
     def precision(self) -> int:
         return int(self._lib.ttsb_engine_get_precision(self._h))
 
+    @_serialised
     def enable_taps(self, on: bool = True):
         _lib.check(self._lib.ttsb_engine_enable_taps(self._h, int(on)))
 
@@ -103,6 +119,7 @@ class Engine:
 
     PROFILE_CATEGORIES = ("conv_tensor", "conv_fp32", "lstm", "istft", "upsample_add", "gather")
 
+    @_serialised
     def profile(self, on: bool = True):
         _lib.check(self._lib.ttsb_engine_profile(self._h, int(on)))
 
@@ -114,6 +131,7 @@ class Engine:
             out[name] = dict(ms=ms.value, flops=fl.value, bytes=by.value, launches=int(n.value))
         return out
 
+    @_serialised
     def read_tap(self, name: str) -> torch.Tensor:
         rows, cols = C.c_int64(), C.c_int64()
         _lib.check(self._lib.ttsb_engine_read_tap(self._h, name.encode(), None, C.byref(rows), C.byref(cols)))
@@ -122,6 +140,7 @@ class Engine:
         return torch.from_numpy(out)
 
     # ------------------------------------------------------------------------------------------------
+    @_serialised
     def synthesize(self, ids_list: Sequence[Sequence[int]], ref_s: torch.Tensor, speeds: Optional[Sequence[float]] = None,
                    noise: Optional[Sequence[torch.Tensor]] = None, seed: int = 0, padded_lstm: bool = True,
                    want_indices: bool = False, forced_dur: Optional[Sequence[Sequence[int]]] = None,
@@ -185,6 +204,7 @@ class Engine:
                 res.indices.append(torch.from_numpy(idx[f_off[b]: f_off[b + 1]].astype(np.int64)))
         return res
 
+    @_serialised
     def vocoder(self, x: torch.Tensor, s: torch.Tensor, f0: torch.Tensor, noise: Optional[torch.Tensor] = None, seed: int = 0,
                 lengths: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
         """Generator only (BASELINE config 4), kokoro layout in: x [B,512,L], s [B,128], f0 [B,L], noise [B,300L,9].
@@ -209,6 +229,7 @@ class Engine:
         return [audio[300 * int(off[b]): 300 * int(off[b + 1])] for b in range(B)]
 
     # ---- single kernels (unit parity / roofline) ------------------------------------------------------
+    @_serialised
     def op_istft(self, cp: torch.Tensor, frames_F: Sequence[int], timed: bool = False):
         """cp [sum(120F+1), ld>=22] device fp32 -> audio [600 sum F]"""
         fc = np.asarray(frames_F, np.int32)
@@ -218,6 +239,7 @@ class Engine:
         _lib.check(self._lib.ttsb_op_istft(self._h, _ptr(cp), cp.shape[1], _ptr(fc), len(fc), _ptr(audio), C.byref(ms)))
         return (audio, ms.value) if timed else audio
 
+    @_serialised
     def op_adain_snake(self, x: torch.Tensor, row_offsets: Sequence[int], gamma_beta: torch.Tensor, alpha: torch.Tensor, timed: bool = False):
         off = np.asarray(row_offsets, np.int32)
         y = torch.empty_like(x)
@@ -227,6 +249,7 @@ class Engine:
                                                  C.byref(ms0), C.byref(ms1)))
         return (y, ms0.value, ms1.value) if timed else y
 
+    @_serialised
     def op_length_regulate(self, pred_dur: torch.Tensor, token_offsets: Sequence[int], src: torch.Tensor, total_frames: int, timed: bool = False):
         off = np.asarray(token_offsets, np.int32)
         B = len(off) - 1
@@ -239,6 +262,7 @@ class Engine:
                                                      C.byref(ms)))
         return (idx, dst, f_off, ms.value) if timed else (idx, dst, f_off)
 
+    @_serialised
     def op_conv1d(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], row_offsets: Sequence[int], dilation: int = 1,
                   precision: int = PRECISION_FP32, reps: int = 1, timed: bool = False):
         """x [sum rows, Cin] device; w [Cout,Cin,k] (torch layout, any device); 'same' zero padding per utterance."""
@@ -253,6 +277,7 @@ class Engine:
                                             int(precision), reps, C.byref(ms)))
         return (y, ms.value) if timed else y
 
+    @_serialised
     def op_bilstm(self, x: torch.Tensor, lstm_state: Mapping[str, torch.Tensor], row_offsets: Sequence[int], timed: bool = False):
         """x [sum rows, In] device; lstm_state = state_dict of an nn.LSTM(In, 256, bidirectional=True)."""
         off = np.asarray(row_offsets, np.int32)

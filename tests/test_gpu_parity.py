@@ -240,6 +240,71 @@ def test_service_is_a_pure_scheduler_and_batch_invariant(checkpoint, oracle):
         assert done == sorted(done)
 
 
+def test_concurrent_callers_on_one_engine_take_turns(engine):
+    """a synthesis is a begin -> finish pair with the workspace in between; two threads on ONE engine (the reference reaches its
+    model through asyncio.to_thread from several places) must each get exactly what they would get alone"""
+    import threading
+    engine.set_precision(pkg.PRECISION_FP16)
+    try:
+        g = torch.Generator().manual_seed(31)
+        jobs = [small_batch([int(n) for n in torch.randint(8, 90, (int(b),), generator=g)], seed=100 + k) for k, b in enumerate([1, 4, 2, 6, 3, 5, 1, 4])]
+        alone = [engine.synthesize(w["ids"], w["ref_s"], w["speeds"], seed=k, padded_lstm=False) for k, w in enumerate(jobs)]
+        got, errs = [None] * len(jobs), []
+
+        def worker(ks):
+            try:
+                for _ in range(3):
+                    for k in ks:
+                        got[k] = engine.synthesize(jobs[k]["ids"], jobs[k]["ref_s"], jobs[k]["speeds"], seed=k, padded_lstm=False)
+            except Exception as exc:                      # pragma: no cover
+                errs.append(exc)
+        th = [threading.Thread(target=worker, args=(list(range(i, len(jobs), 2)),)) for i in range(2)]
+        [t.start() for t in th]
+        [t.join(120) for t in th]
+        assert not errs and not any(t.is_alive() for t in th), errs
+        for k in range(len(jobs)):
+            assert all(torch.equal(a, b) for a, b in zip(alone[k].pred_dur, got[k].pred_dur))
+            assert all(torch.equal(a, b) for a, b in zip(alone[k].audio, got[k].audio)), f"job {k} differs under concurrency"
+    finally:
+        engine.set_precision(pkg.PRECISION_FP32)
+
+
+def test_service_isolates_a_request_the_engine_refuses(checkpoint):
+    """a request of more than 510 symbols is refused by the engine itself (E_TOO_LONG, like kokoro's assert); the service
+    bisects the failed call: that request is FAILED, its neighbours are served by the SAME engine right after the error and get
+    what they get alone (sample counts equal, waveform > 100 dB)"""
+    import asyncio
+
+    from illufly_tts_b200.service import voice_row
+    model = pkg.BatchKModel(config=synthetic_config(), model=checkpoint, precision=pkg.PRECISION_FP16, strict=True, padded_lstm=False).to("cuda:0")
+    voices = {"a": synthetic_voice_pack(1)}
+    g = torch.Generator().manual_seed(41)
+    lens = [20, 55, 600, 33, 70, 12, 48]
+    ph = [ids_to_phonemes(random_ids(g, n)) for n in lens]
+
+    async def main():
+        svc = pkg.TTSServiceManager(model, voices, token_budget=5000)
+        tids = [await svc.submit_task(p, "a", 1.0, user_id=f"u{k}") for k, p in enumerate(ph)]
+        await svc.start()
+        for t in tids:
+            try:
+                async for _ in svc.stream_result(t):
+                    pass
+            except ValueError:
+                pass
+        await svc.stop()
+        return svc, tids
+    svc, tids = asyncio.run(main())
+    st = [svc.tasks[t].status for t in tids]
+    assert st[2] == pkg.TaskStatus.FAILED and svc.tasks[tids[2]].error
+    assert all(x == pkg.TaskStatus.COMPLETED for k, x in enumerate(st) if k != 2), [svc.tasks[t].error for t in tids]
+    assert svc.batch_log and len(svc.batch_log) >= 2                     # the halves that succeeded after the refused call
+    for k in (0, 1, 3, 6):
+        solo = model.forward_batch([ph[k]], voice_row(voices["a"], len(ph[k])).unsqueeze(0), [1.0])[0]
+        mine = svc.tasks[tids[k]].audio_chunks[0]
+        assert solo.numel() == mine.numel() and snr_db(solo.cpu(), mine.cpu()) > 100.0
+
+
 # ---------------------------------------------------------------------------------------------------------
 # single kernels
 # ---------------------------------------------------------------------------------------------------------
