@@ -92,6 +92,10 @@ TTSB_API int ttsb_engine_last_step_ms(ttsb_engine* e, float* ms);
 TTSB_API int ttsb_engine_profile(ttsb_engine* e, int on);
 TTSB_API int ttsb_engine_profile_read(ttsb_engine* e, int category, double* ms, double* flops, double* bytes, int64_t* launches);
 
+/* Threading: a ttsb_engine owns one CUDA stream and one workspace, and begin() ... finish() is a pair with state in between
+ * (the host needs pred_dur to size the frame side).  Calls on ONE engine must not overlap: serialise them (the Python Engine
+ * holds a lock across the pair) or create one engine per thread.  Different engines are independent.  A refused call
+ * (TTSB_E_TOO_LONG, TTSB_E_INVALID, ...) leaves the engine usable for the next one. */
 /* ---- the hot path, two-phase because the number of frames is data-dependent ---------------------------
  * replaces: BatchKModel.forward_batch (core/kmodel.py:7-150) and the inherited KModel.forward
  *           (core/pipeline.py:204); ids are already mapped through the vocab and wrapped in 0 ... 0
