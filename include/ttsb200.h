@@ -43,8 +43,9 @@ enum {
   TTSB_E_TOO_LONG = -5   /* an utterance exceeds 512 tokens (ALBERT positions; kokoro asserts the same) */
 };
 
-/* arithmetic of the frame side (decoder + vocoder).  The text side, which decides the integer
- * durations, always runs in fp32. */
+/* arithmetic of the frame side (decoder + vocoder).  The text side, which decides the integer durations, keeps fp32
+ * accuracy in every mode: fp32 FFMA in TTSB_PRECISION_FP32, tcgen05 with split-fp16 operands (x = hi + lo, three MMAs per
+ * K step, fp32-class products) in the two tensor modes; pred_dur is bit-exact against the fp32 reference in all three. */
 enum {
   TTSB_PRECISION_FP32 = 0,   /* CUDA-core fp32 everywhere: waveform within 1e-3 max-abs of the fp32 reference   */
   TTSB_PRECISION_BF16 = 1,   /* tcgen05 (kind::f16) bf16 operands, fp32 accumulate/statistics                    */
