@@ -50,44 +50,120 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and clock-event (throttle) reasons of THIS rank's GPU, sampled every 25 ms while the timed region runs.
+    In-process NVML: initialised before the region, a sample costs microseconds, so even a quarter-second region (10 steps)
+    gets a dozen samples.  (A spawned `nvidia-smi -lms 200` delivered its first row only after its own start-up - on an
+    8-GPU box later than the end of a short region: samples = 0.)  Falls back to nvidia-smi when NVML cannot be used."""
+    REASONS = (("hw_slowdown", ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"), 0x8),
+               ("hw_thermal_slowdown", ("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"), 0x40),
+               ("sw_thermal_slowdown", ("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"), 0x20),
+               ("sw_power_cap", ("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"), 0x4))
+    PERIOD = 0.025
+
+    def __init__(self, index, nvml=None, uuid=None):
+        self.index, self.uuid, self.nvml = index, uuid, nvml
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.h = self.t = self.smi = None
+        self._stop = threading.Event()
+        self.source = None
+
+    # ---- NVML ----
+    def _open_nvml(self):
+        nv = self.nvml
+        if nv is None:
+            import pynvml as nv
+        nv.nvmlInit()
+        h = None
+        if self.uuid:
+            for cand in (self.uuid, self.uuid.encode()):
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(cand)
+                    break
+                except Exception:
+                    h = None
+        if h is None:
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self.nvml, self.h = nv, h
+        self.masks = [(name, next((getattr(nv, a) for a in attrs if hasattr(nv, a)), default)) for name, attrs, default in self.REASONS]
+        self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self._sample()                                       # must work once, or we fall back
+
+    def _sample(self):
+        nv = self.nvml
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        bits = int(self.get_reasons(self.h))
+        for name, mask in self.masks:
+            if bits & mask:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self._stop.wait(self.PERIOD):
+            try:
+                self._sample()
+            except Exception:
+                return
+
+    # ---- nvidia-smi fallback ----
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def _read_smi(self):
+        for line in self.smi.stdout:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                self.sm.append(float(r[1])); self.mx.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
-                        reasons.add(name)
+                        self.reasons.add(name)
             except Exception:
                 pass
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+    def start(self):
+        """call right before the timed region (NVML is opened here if `open()` was not called earlier)"""
+        if self.source is None:
+            self.open()
+        if self.source == "nvml":
+            self.sm.clear(); self.mx.clear(); self.reasons.clear()     # the probe sample of open() was taken outside the region
+            self._sample()
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def open(self):
+        """the slow part (NVML initialisation or the start-up of nvidia-smi), outside the timed region"""
+        try:
+            self._open_nvml()
+            self.source = "nvml"
+        except Exception:
+            self.h = None
+            try:
+                self.smi = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.t = threading.Thread(target=self._read_smi, daemon=True)
+                self.t.start()
+                self.source = "nvidia-smi"
+            except Exception:
+                self.source = "none"
+
+    def stop(self):
+        if self.source == "nvml":
+            try:
+                self._sample()                               # the region's last moment
+            except Exception:
+                pass
+            self._stop.set()
+            if self.t:
+                self.t.join(timeout=1)
+        elif self.source == "nvidia-smi":
+            self.smi.terminate()
+            try:
+                self.smi.wait(timeout=2)
+            except Exception:
+                self.smi.kill()
+        else:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no NVML and no nvidia-smi"], samples=0, source="none")
+        return dict(sm_mhz=statistics.median(self.sm) if self.sm else None, sm_max_mhz=max(self.mx) if self.mx else None,
+                    reasons=sorted(self.reasons), samples=len(self.sm), source=self.source)
 
 
 def make_workload(rank: int):
@@ -176,13 +252,15 @@ def main():
 
     # ---- device-timed steps (value) ----
     eng.profile(True)
+    uid = getattr(torch.cuda.get_device_properties(local), "uuid", None)
+    clocks = ClockSampler(local, uuid=("GPU-" + str(uid)) if uid is not None else None)
+    clocks.open()                                          # NVML initialisation: before the warm-up, far from the timed region
     frames = None
     for _ in range(warmup):
         r = eng.synthesize(w["ids"], w["ref_s"], w["speeds"], noise=None, seed=7)
         frames = [int(a.numel()) // 600 for a in r.audio]
     audio_s = sum(frames) * 600 / SR
     sync_all()
-    clocks = ClockSampler(local)
     clocks.start()
     l0 = eng.launch_count()
     dev_ms, prof_acc = 0.0, {}

@@ -143,3 +143,56 @@ def test_bench_reference_arm_runs_on_cpu():
     import json
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_clock_sampler_nvml_and_fallbacks():
+    """bench.py's clocks field: in-process NVML samples (>= 2 even for an instantaneous region), reasons decoded from the bit
+    mask, device resolved by UUID first; nvidia-smi, then an explicit 'none', when NVML cannot be used"""
+    import importlib.util
+    import time as _t
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeNvml:
+        NVML_CLOCK_SM = 1
+        nvmlClocksEventReasonSwPowerCap = 0x4
+        nvmlClocksEventReasonHwSlowdown = 0x8
+        nvmlClocksEventReasonSwThermalSlowdown = 0x20
+        nvmlClocksEventReasonHwThermalSlowdown = 0x40
+
+        def __init__(self, bits, uuid_ok=True):
+            self.bits, self.uuid_ok, self.by = bits, uuid_ok, None
+
+        def nvmlInit(self): pass
+
+        def nvmlDeviceGetHandleByUUID(self, u):
+            if not self.uuid_ok:
+                raise RuntimeError("no such uuid")
+            self.by = ("uuid", u)
+            return "H"
+
+        def nvmlDeviceGetHandleByIndex(self, i):
+            self.by = ("index", i)
+            return "H"
+
+        def nvmlDeviceGetClockInfo(self, h, k): return 1890
+        def nvmlDeviceGetMaxClockInfo(self, h, k): return 1965
+        def nvmlDeviceGetCurrentClocksEventReasons(self, h): return self.bits
+
+    nv = FakeNvml(0x4 | 0x1)                                 # sw_power_cap + "gpu idle" (not a reason we report)
+    c = bench.ClockSampler(3, nvml=nv, uuid="GPU-abc")
+    c.open(); c.start(); _t.sleep(0.09); out = c.stop()
+    assert out["source"] == "nvml" and nv.by == ("uuid", "GPU-abc")
+    assert out["sm_mhz"] == 1890 and out["sm_max_mhz"] == 1965 and out["reasons"] == ["sw_power_cap"] and out["samples"] >= 4
+    c = bench.ClockSampler(3, nvml=FakeNvml(0x8 | 0x40, uuid_ok=False), uuid="GPU-abc")
+    c.start(); out = c.stop()                                # start() opens on its own; a zero-length region still has 2 samples
+    assert c.nvml.by == ("index", 3) and out["samples"] >= 2 and out["reasons"] == ["hw_slowdown", "hw_thermal_slowdown"]
+
+    class Broken:
+        def nvmlInit(self): raise RuntimeError("no driver")
+    c = bench.ClockSampler(0, nvml=Broken())
+    c.open()
+    assert c.source in ("nvidia-smi", "none")                # here: no nvidia-smi either, or one that prints nothing
+    out = c.stop()
+    assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons", "samples", "source"}
