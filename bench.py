@@ -193,7 +193,8 @@ def run_reference(args, rank, world):
     m = build_oracle(1234)
     w = make_workload(0)
     n_utt = args.ref_utts
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    n_warm = min(max(args.warmup, 0), 1)       # a CPU step is seconds of work: one warm-up step (lazy initialisation), at most 3 timed
+    for _ in range(n_warm):
         cpu_oracle_rate(m, w, 1, threads)
     rates, tot_s, tot_t = [], 0.0, 0.0
     for _ in range(max(1, min(args.steps, 3))):
@@ -201,9 +202,10 @@ def run_reference(args, rank, world):
         rates.append(r); tot_s += secs; tot_t += dt
     value = tot_s / tot_t
     sample = f"first {n_utt} of the 32 utterances of configs[1] per step ({tot_s / len(rates):.1f} audio-s), fp32 PyTorch CPU eager, per-sample decode loop as kmodel.py:108-144"
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(rates), warmup=args.warmup, ms_per_step=1e3 * tot_t / len(rates),
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=len(rates), warmup=n_warm, ms_per_step=1e3 * tot_t / len(rates),
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload="configs[1]: batch of 32 short utterances (60-90 symbols), one voice; bounded sample", sample_utterances=n_utt),
+                config=dict(workload="configs[1]: batch of 32 short utterances (60-90 symbols), one voice; bounded sample", sample_utterances=n_utt,
+                            requested=dict(steps=args.steps, warmup=args.warmup), bounded="steps <= 3, warmup <= 1: every CPU step is seconds of work"),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
