@@ -301,8 +301,16 @@ def main():
         for _ in range(4):
             _, ms_i = eng.op_istft(cp, Fs, timed=True)
             bi = min(bi, ms_i)
-        hbm_ops["istft_standalone"] = dict(bytes=4.0 * (22 * cp.shape[0] + 600 * sum(Fs)), ms=bi)
+        hbm_ops["istft_standalone"] = dict(bytes=4.0 * (22 * cp.shape[0] + 600 * sum(Fs)), ms=bi)      # the step's amount of data: ~half ramp and tail
         del xb, cp
+        Fs = [1100] * 128                                           # 16x the step's data (1.8 GB): the kernel's steady-state rate
+        cp = torch.randn(sum(120 * f + 1 for f in Fs), 24, device="cuda", generator=g) * 0.5
+        bi = 1e9
+        for _ in range(4):
+            _, ms_i = eng.op_istft(cp, Fs, timed=True)
+            bi = min(bi, ms_i)
+        hbm_ops["istft_streaming_1p8GB"] = dict(bytes=4.0 * (22 * cp.shape[0] + 600 * sum(Fs)), ms=bi)
+        del cp
     # ---- end to end through the reference-facing class (e2e) ----
     for _ in range(2):
         [a.cpu() for a in model.forward_batch(w["phonemes"], ref_pinned, w["speeds"])]
@@ -339,6 +347,9 @@ def main():
         roofline = dict(bound="tensor", kernel=("conv_umma_kernel (tcgen05 implicit-GEMM Conv1d)" if dom == "conv_tensor" else "conv_simt_kernel (fp32 FFMA implicit-GEMM Conv1d)"),
                         achieved=ach, peak=peaks["tf_sustained"], unit="TFLOP/s", frac=ach / peaks["tf_sustained"], traffic=traffic, traffic_note=traffic_note,
                         peak_source=f"bf16 sustained, {peaks['source']}", launches_per_step=p["launches"] / args.steps,
+                        # the same kernel on the other axis: algorithmic bytes (inputs + outputs + residuals, from the launch arguments) per second
+                        hbm_achieved_gbs=(p["bytes"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0),
+                        hbm_frac=(p["bytes"] / (p["ms"] * 1e-3) / 1e9 / peaks["hbm"] if p["ms"] > 0 else 0.0),
                         avg_launch_ms=p["ms"] / max(p["launches"], 1), share_of_step=p["ms"] / max(dev_ms, 1e-9))
         hbm = {}
         for k in ("istft", "upsample_add", "gather"):

