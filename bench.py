@@ -311,6 +311,17 @@ def main():
             bi = min(bi, ms_i)
         hbm_ops["istft_streaming_1p8GB"] = dict(bytes=4.0 * (22 * cp.shape[0] + 600 * sum(Fs)), ms=bi)
         del cp
+        # length-regulation gather at a streaming size (512 utterances x 300 tokens, C = 640: 1.8 GB); `gather` above is the step's own
+        # 23-29 MB, where the two launches (index map + gather) are almost all ramp
+        Bg, Tg, Cg = 512, 300, 640
+        dur = torch.randint(1, 7, (Bg * Tg,), generator=torch.Generator().manual_seed(3), dtype=torch.int32).cuda()
+        srcg = torch.randn(Bg * Tg, Cg, device="cuda", generator=g)
+        Fg = int(dur.sum())
+        bg = 1e9
+        for _ in range(4):
+            bg = min(bg, eng.op_length_regulate(dur, [Tg * b for b in range(Bg + 1)], srcg, Fg, timed=True)[3])
+        hbm_ops["gather_streaming_1p8GB"] = dict(bytes=4.0 * Cg * (Bg * Tg + Fg), ms=bg)
+        del srcg, dur
     # ---- end to end through the reference-facing class (e2e) ----
     for _ in range(2):
         [a.cpu() for a in model.forward_batch(w["phonemes"], ref_pinned, w["speeds"])]

@@ -229,9 +229,22 @@ class Engine:
         return [audio[300 * int(off[b]): 300 * int(off[b + 1])] for b in range(B)]
 
     # ---- single kernels (unit parity / roofline) ------------------------------------------------------
+    def _dev_arg(self, name: str, t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        """The op_* entry points hand raw pointers to kernels: a CPU tensor would be a wild device pointer (illegal address, and the
+        CUDA context is gone), a float64 or strided one would be read as garbage.  Refuse them here with a message instead."""
+        if not isinstance(t, torch.Tensor) or not t.is_cuda or t.device != self.device:
+            where = getattr(t, "device", type(t).__name__)
+            raise ValueError(f"{name} must be a tensor on {self.device} (got {where}): move it with .to('{self.device}')")
+        if t.dtype != dtype:
+            raise ValueError(f"{name} must be {dtype} (got {t.dtype})")
+        if not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous")
+        return t
+
     @_serialised
     def op_istft(self, cp: torch.Tensor, frames_F: Sequence[int], timed: bool = False):
         """cp [sum(120F+1), ld>=22] device fp32 -> audio [600 sum F]"""
+        self._dev_arg("cp", cp, torch.float32)
         fc = np.asarray(frames_F, np.int32)
         audio = torch.empty(600 * int(fc.sum()), dtype=torch.float32, device=self.device)
         ms = C.c_float(0)
@@ -241,6 +254,7 @@ class Engine:
 
     @_serialised
     def op_adain_snake(self, x: torch.Tensor, row_offsets: Sequence[int], gamma_beta: torch.Tensor, alpha: torch.Tensor, timed: bool = False):
+        self._dev_arg("x", x, torch.float32); self._dev_arg("gamma_beta", gamma_beta, torch.float32); self._dev_arg("alpha", alpha, torch.float32)
         off = np.asarray(row_offsets, np.int32)
         y = torch.empty_like(x)
         ms0, ms1 = C.c_float(0), C.c_float(0)
@@ -251,6 +265,7 @@ class Engine:
 
     @_serialised
     def op_length_regulate(self, pred_dur: torch.Tensor, token_offsets: Sequence[int], src: torch.Tensor, total_frames: int, timed: bool = False):
+        self._dev_arg("pred_dur", pred_dur, torch.int32); self._dev_arg("src", src, torch.float32)
         off = np.asarray(token_offsets, np.int32)
         B = len(off) - 1
         idx = torch.empty(total_frames, dtype=torch.int32, device=self.device)
@@ -266,6 +281,7 @@ class Engine:
     def op_conv1d(self, x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], row_offsets: Sequence[int], dilation: int = 1,
                   precision: int = PRECISION_FP32, reps: int = 1, timed: bool = False):
         """x [sum rows, Cin] device; w [Cout,Cin,k] (torch layout, any device); 'same' zero padding per utterance."""
+        self._dev_arg("x", x, torch.float32)
         off = np.asarray(row_offsets, np.int32)
         wn = np.ascontiguousarray(w.detach().to(torch.float32).cpu().numpy())
         bn = None if bias is None else np.ascontiguousarray(bias.detach().to(torch.float32).cpu().numpy())
@@ -280,6 +296,7 @@ class Engine:
     @_serialised
     def op_bilstm(self, x: torch.Tensor, lstm_state: Mapping[str, torch.Tensor], row_offsets: Sequence[int], timed: bool = False):
         """x [sum rows, In] device; lstm_state = state_dict of an nn.LSTM(In, 256, bidirectional=True)."""
+        self._dev_arg("x", x, torch.float32)
         off = np.asarray(row_offsets, np.int32)
 
         def cat(name):
