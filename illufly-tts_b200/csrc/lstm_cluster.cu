@@ -35,6 +35,15 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// two independent IEEE fp32 FMAs in one instruction (SASS FFMA2): (a0, a1) = (w0 h0 + a0, w1 h1 + a1), bit-identical to two fmaf
+__device__ __forceinline__ void fma2(float& a0, float& a1, float w0, float w1, float h0, float h1) {
+  unsigned long long a, w, h;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(w) : "f"(w0), "f"(w1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(h) : "f"(h0), "f"(h1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a) : "l"(w), "l"(h));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+}
 __device__ __forceinline__ uint32_t map_to_peer(uint32_t local_smem_addr, uint32_t peer) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(peer));
@@ -165,7 +174,7 @@ lstm_cluster_kernel(const float* __restrict__ gx, const float* __restrict__ whh,
       for (int r = 0; r < 4; ++r) {
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) { a0 = fmaf(w[r][i], h[i], a0); a1 = fmaf(w[r][i + 1], h[i + 1], a1); }
+        for (int i = 0; i < 16; i += 2) fma2(a0, a1, w[r][i], w[r][i + 1], h[i], h[i + 1]);      // the same two chains, half the instructions
         v[r * 4 + u] = a0 + a1;
       }
     }
