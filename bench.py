@@ -383,7 +383,9 @@ def main():
                              api="BatchKModel.forward_batch(list[str], pinned ref_s [B,1,256], speeds) + .cpu() per waveform"),
                     gpu_launches=int(launches_total), clocks=clk, roofline=roofline, hbm_kernels=hbm,
                     algorithmic_tflops_per_s=algorithmic_flops(tokens, frames) * world / (dev_ms_max / args.steps * 1e-3) / 1e12,
-                    profile_ms_per_step={k: v["ms"] / args.steps for k, v in prof_acc.items()})
+                    profile_ms_per_step={k: v["ms"] / args.steps for k, v in prof_acc.items()},
+                    # share of the device-timed step covered by the event-timed categories (the rest: small kernels, host gap between the halves)
+                    profile_accounted_frac=sum(v["ms"] for v in prof_acc.values()) / max(dev_ms, 1e-9))
         if not args.no_cpu_baseline and world == 1:
             from oracle.synth_weights import build_oracle
             threads = os.cpu_count() or 1

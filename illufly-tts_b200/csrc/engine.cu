@@ -690,7 +690,9 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   if (har) CK(cudaMemsetAsync(har, 0, sizeof(float) * (size_t)totH * 24, r.s));
   float* har_src = e.taps_on ? r.alloc<float>((size_t)spA.total) : nullptr;
   if (!phase || !har) return TTSB_E_NOMEM;
+  r.e.prof.begin(r.s, PROF_SOURCE, 0.0, 0.0);
   CK(launch_source_stft(f0, noise, e.src_lin_w, e.src_lin_b, har_src, har, 24, phase, tL_S1.segs, nseg, spL.maxlen, seed, seg_seeds, r.s));
+  r.e.prof.end(r.s);
   if (har_src) RC(r.tap("har_source", har_src, spA.total, 1, 1));
   RC(r.tap_ragged("har", har, 22, 24, offH, lenH));
 
@@ -840,16 +842,24 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   float* TMP = r.alloc<float>((size_t)R * 768);
   float* FF = r.alloc<float>((size_t)R * 2048);
   if (!E || !H || !QKV || !CTX || !A1 || !TMP || !FF) return TTSB_E_NOMEM;
+  r.e.prof.begin(r.s, PROF_LAYERNORM, 0.0, 0.0);
   CK(launch_albert_embed(d_ids, d_pos, e.emb_word, e.emb_pos, e.emb_type, e.emb_ln_g, e.emb_ln_b, E, R, r.s));
+  r.e.prof.end(r.s);
   { ConvCall c; c.w = &e.map_in; c.x = E; c.ldx = 128; c.y = H; c.ldy = 768; c.exact = true; RC(run_conv(r, c, tTf)); }
   for (int layer = 0; layer < 12; ++layer) {
     { ConvCall c; c.w = &e.qkv; c.x = H; c.ldx = 768; c.y = QKV; c.ldy = 2304; c.exact = true; RC(run_conv(r, c, tTf)); }
+    r.e.prof.begin(r.s, PROF_ATTENTION, 0.0, 0.0);
     CK(launch_attention(QKV, CTX, tT.segs, B, e.spT.maxlen, 12, r.s));
+    r.e.prof.end(r.s);
     { ConvCall c; c.w = &e.att_dense; c.x = CTX; c.ldx = 768; c.y = TMP; c.ldy = 768; c.res = H; c.ldr = 768; c.exact = true; RC(run_conv(r, c, tTf)); }
+    r.e.prof.begin(r.s, PROF_LAYERNORM, 0.0, 8.0 * (double)(R) * (double)(768));
     CK(launch_layernorm(TMP, 768, nullptr, 0, A1, 768, R, 768, 1e-12f, 0, e.att_ln_g, e.att_ln_b, nullptr, 0, nullptr, ACT_NONE, 0.f, r.s));
+    r.e.prof.end(r.s);
     { ConvCall c; c.w = &e.ffn; c.x = A1; c.ldx = 768; c.y = FF; c.ldy = 2048; c.act = ACT_GELU_NEW; c.exact = true; RC(run_conv(r, c, tTf)); }
     { ConvCall c; c.w = &e.ffn_out; c.x = FF; c.ldx = 2048; c.y = TMP; c.ldy = 768; c.res = A1; c.ldr = 768; c.exact = true; RC(run_conv(r, c, tTf)); }
+    r.e.prof.begin(r.s, PROF_LAYERNORM, 0.0, 8.0 * (double)(R) * (double)(768));
     CK(launch_layernorm(TMP, 768, nullptr, 0, H, 768, R, 768, 1e-12f, 0, e.full_ln_g, e.full_ln_b, nullptr, 0, nullptr, ACT_NONE, 0.f, r.s));
+    r.e.prof.end(r.s);
   }
   RC(r.tap("bert", H, R, 768, 768));
 
@@ -863,7 +873,9 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   RC(r.tap("d_en", X, R, 512, 640));
   for (int l = 0; l < 3; ++l) {
     RC(run_bilstm(r, e.de_lstm[l], X, 640, GX, Y, 512, tTf, d_ls, n_ls, true));
+    r.e.prof.begin(r.s, PROF_LAYERNORM, 0.0, 8.0 * (double)(R) * (double)(512));
     CK(launch_layernorm(Y, 512, nullptr, 0, X, 640, R, 512, 1e-5f, 1, nullptr, nullptr, e.d_gbP + e.de_aln[l].off, ldP, d_r2s, ACT_NONE, 0.f, r.s));
+    r.e.prof.end(r.s);
   }
   RC(r.tap("d", X, R, 640, 640));
   e.d_X = X;
@@ -897,7 +909,9 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   for (int l = 0; l < 3; ++l) {
     ConvCall c; c.w = &e.te_cnn[l]; c.x = TE0; c.ldx = 512; c.y = TE1; c.ldy = 512; c.pad = 2; c.exact = true;
     RC(run_conv(r, c, tT));
+    r.e.prof.begin(r.s, PROF_LAYERNORM, 0.0, 8.0 * (double)(R) * (double)(512));
     CK(launch_layernorm(TE1, 512, nullptr, 0, TE0, 512, R, 512, 1e-5f, 0, e.te_ln_g[l], e.te_ln_b[l], nullptr, 0, nullptr, ACT_LRELU, 0.2f, r.s));
+    r.e.prof.end(r.s);
   }
   RC(run_bilstm(r, e.te_lstm, TE0, 512, GX, TEN, 512, tTf, d_ls, n_ls, true));
   RC(r.tap("t_en", TEN, R, 512, 512));

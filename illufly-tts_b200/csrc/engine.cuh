@@ -64,7 +64,8 @@ struct SegTab {                           // device tables for one (in space -> 
 struct Tap { float* d = nullptr; int64_t rows = 0, cols = 0; };
 
 // per-category device time of the last step, from CUDA events recorded around the launches on the engine's stream
-enum ProfCat : int { PROF_CONV_TENSOR = 0, PROF_CONV_SIMT = 1, PROF_LSTM = 2, PROF_ISTFT = 3, PROF_ELEMENTWISE = 4, PROF_GATHER = 5, PROF_NCAT = 6 };
+enum ProfCat : int { PROF_CONV_TENSOR = 0, PROF_CONV_SIMT = 1, PROF_LSTM = 2, PROF_ISTFT = 3, PROF_ELEMENTWISE = 4, PROF_GATHER = 5, PROF_ATTENTION = 6, PROF_LAYERNORM = 7,
+                     PROF_SOURCE = 8, PROF_NCAT = 9 };
 struct ProfRec { int cat; double flops, bytes; };
 struct Profiler {
   bool on = false;

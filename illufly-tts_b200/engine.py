@@ -117,7 +117,7 @@ class Engine:
         _lib.check(self._lib.ttsb_engine_last_step_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
-    PROFILE_CATEGORIES = ("conv_tensor", "conv_fp32", "lstm", "istft", "upsample_add", "gather")
+    PROFILE_CATEGORIES = ("conv_tensor", "conv_fp32", "lstm", "istft", "upsample_add", "gather", "attention", "layernorm", "harmonic_source")
 
     @_serialised
     def profile(self, on: bool = True):

@@ -89,7 +89,8 @@ TTSB_API int64_t ttsb_engine_launch_count(ttsb_engine* e);
  * begin() (or vocoder()) to the last operation of finish(), host gaps between the two phases included */
 TTSB_API int ttsb_engine_last_step_ms(ttsb_engine* e, float* ms);
 /* per-kernel-category CUDA-event timing of the next steps (bench.py's roofline): category 0 tcgen05 conv, 1 fp32 conv,
- * 2 LSTM recurrence, 3 iSTFT, 4 upsample-add (elementwise), 5 length-regulation gather.  Results are those of the last step. */
+ * 2 LSTM recurrence, 3 iSTFT, 4 upsample-add (elementwise), 5 length-regulation gather, 6 attention, 7 LayerNorm family (ALBERT
+ * embedding LN, LN, AdaLayerNorm), 8 harmonic source (phase scan + SineGen/STFT).  Results are those of the last step. */
 TTSB_API int ttsb_engine_profile(ttsb_engine* e, int on);
 TTSB_API int ttsb_engine_profile_read(ttsb_engine* e, int category, double* ms, double* flops, double* bytes, int64_t* launches);
 
