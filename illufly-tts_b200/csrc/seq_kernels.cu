@@ -23,7 +23,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int MAXV = 24;  // 768 / 32
 
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ res, int ldr,
+__global__ void __launch_bounds__(256, 2) layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ res, int ldr,
                                                         float* __restrict__ out, int ldo, int rows, int C, float eps, int mode,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         const float* __restrict__ gb, int ld_gb, const int* __restrict__ row2seg,
@@ -31,16 +31,46 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  float v[MAXV];
+  // Every load of a pass is issued before anything waits on one.  A warp issues in order, and a load behind `if (c < C)` (C is a
+  // run-time value) cannot be hoisted above its branch: with the loads inside the element loop, the 24 loads of a lane were 24
+  // SERIAL round trips (ncu: 88 % of the stalls on the long scoreboard at two lines, 10 % of the issue slots busy, 22 us for a
+  // 15-MB LayerNorm).  The addresses are clamped into the row instead and the value is selected afterwards; the arithmetic and its
+  // order are unchanged, so the results are bit-identical.
+  const int seg = (mode == 1) ? row2seg[row] : 0;
+  const float* gp = (mode == 1) ? gb + (size_t)seg * ld_gb : gamma;          // scale row (AdaLayerNorm: gamma | beta of the utterance)
+  const float* bp = (mode == 1) ? gb + (size_t)seg * ld_gb + C : beta;
+  const bool affine = (mode == 1) || gamma != nullptr;
+  float v[MAXV], gv[MAXV], bv[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    const int cc = c < C ? c : C - 1;
+    v[i] = x[(size_t)row * ldx + cc];
+  }
+  if (res) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      const int cc = c < C ? c : C - 1;
+      gv[i] = res[(size_t)row * ldr + cc];                 // borrowed as a temporary
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) v[i] += gv[i];
+  }
+  if (affine) {                                            // in flight during the two reductions below
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = lane + i * 32;
+      const int cc = c < C ? c : C - 1;
+      gv[i] = gp[cc];
+      bv[i] = bp[cc];
+    }
+  }
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + i * 32;
-    float t = 0.f;
-    if (c < C) {
-      t = x[(size_t)row * ldx + c];
-      if (res) t += res[(size_t)row * ldr + c];
-    }
+    const float t = c < C ? v[i] : 0.f;
     v[i] = t;
     s += t;
   }
@@ -53,16 +83,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
   const float var = warp_sum(q) / (float)C;
   const float rstd = 1.0f / sqrtf(var + eps);
-  const int seg = (mode == 1) ? row2seg[row] : 0;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + i * 32;
     if (c < C) {
       float y = (v[i] - mean) * rstd;
       if (mode == 1) {
-        y = (1.0f + gb[(size_t)seg * ld_gb + c]) * y + gb[(size_t)seg * ld_gb + C + c];
+        y = (1.0f + gv[i]) * y + bv[i];
       } else {
-        if (gamma) y = y * gamma[c] + beta[c];
+        if (gamma) y = y * gv[i] + bv[i];
       }
       if (act == ACT_LRELU) y = lrelu(y, slope);
       out[(size_t)row * ldo + c] = y;
