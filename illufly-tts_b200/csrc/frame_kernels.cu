@@ -1,6 +1,8 @@
 // Frame-side bandwidth-bound kernels: per-utterance channel statistics, AdaIN+Snake, depthwise x2 transposed
 // conv, the NSF harmonic source + STFT(20,5), upsample-add, and the fused exp/sin + iSTFT(20,5) overlap-add.
 // All of them are single coalesced passes over channels-last rows; the roofline that bounds them is HBM.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include <curand_kernel.h>
 #include <math.h>
@@ -175,7 +177,8 @@ __global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* 
 // NSF harmonic source (A.11): phase scan.  One thread per (utterance, harmonic): torch.cumsum on CPU accumulates
 // fp32 inputs in fp64 and rounds each prefix to fp32, then *2, *pi, *300 in fp32.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void phase_scan_kernel(const float* __restrict__ f0, float* __restrict__ phase, const Seg* __restrict__ segs, int nseg) {
+// serial form (one thread per utterance and harmonic): the reference order, kept behind TTSB_PHASE_SERIAL=1 for bit-for-bit checks
+__global__ void phase_scan_serial_kernel(const float* __restrict__ f0, float* __restrict__ phase, const Seg* __restrict__ segs, int nseg) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nseg * 9) return;
   const int sgi = idx / 9, h = idx % 9;
@@ -192,6 +195,47 @@ __global__ void phase_scan_kernel(const float* __restrict__ f0, float* __restric
     float p = __fmul_rn(__fmul_rn(cs, 2.0f), 3.14159274101257324f);
     p = __fmul_rn(p, 300.0f);
     phase[(size_t)(seg.in_off + d) * 9 + h] = p;
+  }
+}
+
+// One WARP per (utterance, harmonic): the frames in chunks of 32, a shuffle prefix sum of the per-frame terms in double, the
+// chunk's carry added on top.  The per-frame term m = fmod(f0 h / 24000, 1) is the same float as in the serial form; the only
+// thing that changes is the ORDER of the double additions, and those are exact: m is a float in [0, 1) - a multiple of 2^-32 or
+// coarser for any f0 h above ~0.01 Hz - and the partial sums stay below 2^9, so every partial sum is representable in 53 bits and
+// association does not matter (below that, a difference of 2^-53 relative could appear, and disappears in the cast to float).
+// Bit-for-bit equality with the serial form is a test (test_phase_scan_parallel_equals_serial).  The serial form took 159 us for
+// 275 frames - one global-load round trip per frame on 5 of the 148 SMs - at batch 32 and just as long for a single utterance.
+__global__ void __launch_bounds__(128) phase_scan_kernel(const float* __restrict__ f0, float* __restrict__ phase, const Seg* __restrict__ segs, int nseg) {
+  const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= nseg * 9) return;
+  const int sgi = wid / 9, h = wid % 9;
+  const Seg seg = segs[sgi];
+  const float hm = (float)(h + 1);
+  double carry = 0.0;
+  for (int d0 = 0; d0 < seg.in_len; d0 += 32) {
+    const int d = d0 + lane;
+    float m = 0.f;
+    if (d < seg.in_len) {
+      const float fn = __fmul_rn(f0[seg.in_off + d], hm);
+      const float q = __fdiv_rn(fn, 24000.0f);
+      m = fmodf(q, 1.0f);
+      if (m != 0.f && m < 0.f) m = __fadd_rn(m, 1.0f);        // python-style remainder, as c10 does it
+    }
+    double v = (double)m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += up;
+    }
+    const double acc = carry + v;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+    if (d < seg.in_len) {
+      const float cs = (float)acc;
+      float p = __fmul_rn(__fmul_rn(cs, 2.0f), 3.14159274101257324f);
+      p = __fmul_rn(p, 300.0f);
+      phase[(size_t)(seg.in_off + d) * 9 + h] = p;
+    }
   }
 }
 
@@ -477,7 +521,9 @@ cudaError_t launch_source_stft(const float* f0, const float* noise, const float*
   cudaError_t e = ensure_tables();
   if (e != cudaSuccess) return e;
   float* phase = scratch_phase;
-  phase_scan_kernel<<<(nseg * 9 + 63) / 64, 64, 0, s>>>(f0, phase, segs, nseg);
+  static const bool serial = getenv("TTSB_PHASE_SERIAL") != nullptr;
+  if (serial) phase_scan_serial_kernel<<<(nseg * 9 + 63) / 64, 64, 0, s>>>(f0, phase, segs, nseg);
+  else phase_scan_kernel<<<(nseg * 9 + 3) / 4, 128, 0, s>>>(f0, phase, segs, nseg);
   if ((e = launched()) != cudaSuccess) return e;
   const int max_frames = 60 * max_L + 1;
   dim3 grid((max_frames + SF - 1) / SF, nseg);

@@ -305,6 +305,30 @@ def test_service_isolates_a_request_the_engine_refuses(checkpoint):
         assert solo.numel() == mine.numel() and snr_db(solo.cpu(), mine.cpu()) > 100.0
 
 
+def test_phase_scan_parallel_equals_serial(tmp_path):
+    """the harmonic phase is an integrator: the warp-parallel prefix sum must give the SAME floats as the
+    serial running sum of the reference order.  It does because the additions are exact in double (frame_kernels.cu); here both
+    forms run on BASELINE configs[1] and on utterances of 1, 33 and 510 symbols, and the audio-rate harmonic source and the
+    waveforms must be bit-identical."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for mode in ("parallel", "serial"):
+        env = dict(os.environ)
+        env.pop("TTSB_PHASE_SERIAL", None)
+        if mode == "serial":
+            env["TTSB_PHASE_SERIAL"] = "1"
+        f = str(tmp_path / f"{mode}.pt")
+        subprocess.run([sys.executable, os.path.join(root, "tests", "dump_source.py"), f], check=True, env=env, cwd=root, timeout=300,
+                       stdout=subprocess.DEVNULL)
+        outs[mode] = torch.load(f)
+    for k in outs["serial"]:
+        assert torch.equal(outs["serial"][k], outs["parallel"][k]), f"{k} differs between the serial and the parallel phase scan"
+    assert outs["serial"]["b32_src"].abs().max() > 0.01
+
+
 # ---------------------------------------------------------------------------------------------------------
 # single kernels
 # ---------------------------------------------------------------------------------------------------------
