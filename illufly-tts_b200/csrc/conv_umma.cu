@@ -795,7 +795,10 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const ConvArgs p, int KS,
     }
     __syncthreads();
   }
-  for (int idx = threadIdx.x; idx < planes * SR; idx += blockDim.x) {
+  // one item (8 channels of one row) per thread: blockIdx.z covers the rows.  With a loop of 4-8 items per thread every iteration
+  // was a global-load round trip of its own (load inside a branch, dependent conversion and store behind it): ~10 us per launch
+  // for a few MB, 73 launches per step
+  for (int idx = blockIdx.z * blockDim.x + threadIdx.x; idx < planes * SR; idx += gridDim.z * blockDim.x) {
     const int r = idx % SR, pln = idx / SR;
     const int c0 = sc * KS + pln * 8;
     const int traw = tile.t0 + r - p.pad;
@@ -1004,7 +1007,8 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     static const PackFn ptable[4][3] = {
         {pack_act_kernel<0, 0>, pack_act_kernel<0, 1>, pack_act_kernel<0, 2>}, {pack_act_kernel<1, 0>, pack_act_kernel<1, 1>, pack_act_kernel<1, 2>},
         {pack_act_kernel<2, 0>, pack_act_kernel<2, 1>, pack_act_kernel<2, 2>}, {pack_act_kernel<3, 0>, pack_act_kernel<3, 1>, pack_act_kernel<3, 2>}};
-    ptable[a.pro][a.wfmt]<<<dim3(a.ntiles, u.p.nsc), 256, 0, s>>>(u.a, u.p.KS, u.p.nsc, u.p.SR, u.p.slab_bytes, a.xpack);
+    const int pack_items = (u.p.KS >> 3) * u.p.SR;
+    ptable[a.pro][a.wfmt]<<<dim3(a.ntiles, u.p.nsc, (pack_items + 255) / 256), 256, 0, s>>>(u.a, u.p.KS, u.p.nsc, u.p.SR, u.p.slab_bytes, a.xpack);
     cudaError_t e = launched();
     if (e != cudaSuccess) return e;
     u.xpack = a.xpack;
