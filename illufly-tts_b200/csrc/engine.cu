@@ -916,6 +916,11 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   RC(run_bilstm(r, e.te_lstm, TE0, 512, GX, TEN, 512, tTf, d_ls, n_ls, true));
   RC(r.tap("t_en", TEN, R, 512, 512));
   e.d_ten = TEN;
+  static const bool gap_prof = getenv("TTSB_GAP_PROF") != nullptr;
+  if (gap_prof) {                       // the last work of this half: the text encoder, queued to overlap the host's part
+    if (!e.ev_gap0) { CK(cudaEventCreate(&e.ev_gap0)); CK(cudaEventCreate(&e.ev_gap1)); }
+    CK(cudaEventRecord(e.ev_gap0, r.s));
+  }
 
   CK(cudaEventSynchronize(e.ev0));
   std::vector<int> fl(B);
@@ -961,6 +966,13 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   const LstmGroup* d_lsF = r.push(g_lsF);
   RC(r.tables_upload());
   RC(r.stats_begin(B, 40960));
+  if (e.ev_gap0 && getenv("TTSB_GAP_PROF")) {
+    // idle time of the GPU between the halves: from the end of begin()'s queued work to the point where finish() can launch
+    CK(cudaEventRecord(e.ev_gap1, r.s));
+    CK(cudaEventSynchronize(e.ev_gap1));
+    float gap = 0.f;
+    if (cudaEventElapsedTime(&gap, e.ev_gap0, e.ev_gap1) == cudaSuccess) fprintf(stderr, "ttsb: GPU idle between begin() and finish(): %.3f ms\n", gap);
+  }
 
   // noise for SineGen
   const float* d_noise = nullptr;

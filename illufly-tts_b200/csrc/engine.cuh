@@ -116,6 +116,7 @@ struct Engine {
   Profiler prof;
   int precision = 0;
   bool taps_on = false;
+  cudaEvent_t ev_gap0 = nullptr, ev_gap1 = nullptr;   // TTSB_GAP_PROF=1: GPU idle time between the two halves of a step
   std::vector<unsigned long long> utt_key;   // per utterance of the step in flight: hash of its token ids (begin -> finish)
   bool finalized = false;
   std::map<std::string, HostTensor> host;       // raw checkpoint tensors until finalize()
