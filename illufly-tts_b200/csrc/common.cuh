@@ -72,6 +72,10 @@ inline cudaError_t launched(int n = 1) { __sync_fetch_and_add(&g_launches, (long
 
 // ---- kernel launchers (each returns the launch error) -------------------------------------------------
 cudaError_t launch_conv_simt(const ConvArgs& a, cudaStream_t s);
+cudaError_t launch_rowdot(const float* x, int ldx, int rows, int C, const float* w, int ldw, const float* bias, float* y, int ldy,
+                          cudaStream_t s);            // y[r] = bias + sum_c x[r][c] w[c]: Conv1d(C, 1, 1) over flat rows
+cudaError_t launch_style_proj(const float* style, int ld_style, int nseg, const float* w, int ldw, const float* bias, float* out, int ldo, int K,
+                              int N, cudaStream_t s);   // out[b][n] = bias[n] + sum_k style[b][k] w[k][n], a few rows b
 cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s);     // tcgen05 bf16 path (k*dil halo, Cin%16==0 after padding)
 bool conv_umma_supported(const ConvArgs& a);
 

@@ -215,7 +215,103 @@ __global__ void __launch_bounds__(NT, 2) conv_simt_kernel(const ConvArgs p) {
     }
   }
 }
+
+// Style projection: out[b][n] = bias[n] + sum_k style[b][k] W[k][n] for a HANDFUL of rows b (one per utterance) and tens of thousands
+// of columns n (every AdaIN / AdaLayerNorm `fc` of a style half side by side).  One thread per column, the style rows transposed in
+// shared memory ([k][32 utterances]: one 16-B load serves four utterances), weight reads coalesced over n and issued eight k ahead.
+// Same arithmetic as conv_simt_kernel gives for this shape - acc = 0, acc = fmaf(x_k, w_k, acc) for ascending k, + bias - so the
+// outputs are bit-identical (they become the scales and shifts that decide the integer durations: tested).  The 128 x 128-tile
+// kernel spent 82 us on it with a quarter of its rows valid at batch 32 (and one row at batch 1), twice per step.
+constexpr int SP_K = 128;
+__global__ void __launch_bounds__(256) style_proj_kernel(const float* __restrict__ style, int ld_style, int nseg, const float* __restrict__ w, int ldw,
+                                                         const float* __restrict__ bias, float* __restrict__ out, int ldo, int K, int N) {
+  __shared__ __align__(16) float s_t[SP_K][32];
+  const int n = blockIdx.x * 256 + threadIdx.x;
+  const int nc = n < N ? n : N - 1;                       // clamped: every load is valid, the store is guarded
+  for (int b0 = 0; b0 < nseg; b0 += 32) {
+    const int nb = min(32, nseg - b0);
+    for (int i = threadIdx.x; i < SP_K * 32; i += 256) {
+      const int k = i >> 5, b = i & 31;
+      s_t[k][b] = (k < K && b < nb) ? style[(size_t)(b0 + b) * ld_style + k] : 0.f;
+    }
+    __syncthreads();
+    float acc[32];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      float wv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) wv[j] = (k0 + j < K) ? w[(size_t)(k0 + j) * ldw + nc] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (k0 + j < K) {
+#pragma unroll
+          for (int b4 = 0; b4 < 8; ++b4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(&s_t[k0 + j][4 * b4]);
+            acc[4 * b4 + 0] = fmaf(s4.x, wv[j], acc[4 * b4 + 0]);
+            acc[4 * b4 + 1] = fmaf(s4.y, wv[j], acc[4 * b4 + 1]);
+            acc[4 * b4 + 2] = fmaf(s4.z, wv[j], acc[4 * b4 + 2]);
+            acc[4 * b4 + 3] = fmaf(s4.w, wv[j], acc[4 * b4 + 3]);
+          }
+        }
+      }
+    }
+    if (n < N) {
+      const float bn = bias ? bias[n] : 0.f;
+#pragma unroll
+      for (int b = 0; b < 32; ++b)
+        if (b < nb) out[(size_t)(b0 + b) * ldo + n] = bias ? acc[b] + bn : acc[b];
+    }
+    __syncthreads();
+  }
+}
+
+// y[r] = bias + sum_c x[r][c] w[c]: a Conv1d(C, 1, 1) (F0_proj, N_proj) over every row of a space.  A warp stages 32 rows x 32
+// channels through padded shared memory (coalesced 128-B row segments in, conflict-free columns out) and each lane then walks ITS
+// row with one accumulator, channels ascending - the order of conv_simt_kernel, so F0 and N are bit-identical to what the tiled
+// kernel gave (F0 feeds the phase integrator: tested).  The tiled kernel computed 128 output columns to keep one: 82 us per launch.
+__global__ void __launch_bounds__(128) rowdot_kernel(const float* __restrict__ x, int ldx, int rows, int C, const float* __restrict__ w, int ldw,
+                                                     const float* __restrict__ bias, float* __restrict__ y, int ldy) {
+  __shared__ float tile[4][32][33];
+  __shared__ float ws[512];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < C; c += 128) ws[c] = w[(size_t)c * ldw];
+  __syncthreads();
+  const int r0 = (blockIdx.x * 4 + warp) * 32;
+  if (r0 >= rows) return;
+  float acc = 0.f;
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int cc = min(c0 + lane, C - 1);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) tile[warp][i][lane] = x[(size_t)min(r0 + i, rows - 1) * ldx + cc];
+    __syncwarp();
+    const int nj = min(32, C - c0);
+    if (nj == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc = fmaf(tile[warp][lane][j], ws[c0 + j], acc);
+    } else {
+      for (int j = 0; j < nj; ++j) acc = fmaf(tile[warp][lane][j], ws[c0 + j], acc);
+    }
+    __syncwarp();
+  }
+  if (r0 + lane < rows) y[(size_t)(r0 + lane) * ldy] = bias ? acc + bias[0] : acc;
+}
 }  // namespace
+
+cudaError_t launch_style_proj(const float* style, int ld_style, int nseg, const float* w, int ldw, const float* bias, float* out, int ldo, int K,
+                              int N, cudaStream_t s) {
+  if (nseg <= 0 || N <= 0) return cudaSuccess;
+  if (K <= 0 || K > SP_K) return cudaErrorInvalidValue;
+  style_proj_kernel<<<(N + 255) / 256, 256, 0, s>>>(style, ld_style, nseg, w, ldw, bias, out, ldo, K, N);
+  return launched();
+}
+
+cudaError_t launch_rowdot(const float* x, int ldx, int rows, int C, const float* w, int ldw, const float* bias, float* y, int ldy, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  if (C <= 0 || C > 512) return cudaErrorInvalidValue;
+  rowdot_kernel<<<(rows + 127) / 128, 128, 0, s>>>(x, ldx, rows, C, w, ldw, bias, y, ldy);
+  return launched();
+}
 
 cudaError_t launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
   if (a.ntiles <= 0) return cudaSuccess;

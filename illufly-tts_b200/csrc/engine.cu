@@ -753,6 +753,14 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
 int run_style(Run& r, const ConvW& w, const float* style, int ld_style, int nseg, float** out) {
   float* gb = r.alloc<float>((size_t)nseg * w.ldw);
   if (!gb) return TTSB_E_NOMEM;
+  static const bool use_simt = getenv("TTSB_STYLE_SIMT") != nullptr;     // the tiled fp32 conv kernel: kept for bit-for-bit checks
+  if (!use_simt && w.k == 1 && w.Cin <= 128) {
+    r.e.prof.begin(r.s, PROF_CONV_SIMT, 2.0 * nseg * w.Cin * w.Cout, 4.0 * ((double)w.Cin * w.Cout + (double)nseg * w.Cout));
+    CK(launch_style_proj(style, ld_style, nseg, w.w, w.ldw, w.bias, gb, w.ldw, w.Cin, w.Cout, r.s));
+    r.e.prof.end(r.s);
+    *out = gb;
+    return TTSB_OK;
+  }
   Space one; one.build({nseg});
   RC(r.tables_begin(4096));
   const SegTab t = r.make_tab(one, one);
@@ -1023,8 +1031,16 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
     RC(run_resblk1d(r, blk[0], SH, 512, st_sh, o0, 512, s0, gbP, ldP, tF, tF, tF, true));
     RC(run_resblk1d(r, blk[1], o0, 512, s0, o1, 256, s1, gbP, ldP, tF, tL, tFL, true));
     RC(run_resblk1d(r, blk[2], o1, 256, s1, o2, 256, nullptr, gbP, ldP, tL, tL, tL, true));
-    ConvCall c; c.w = br == 0 ? &e.f0_proj : &e.n_proj; c.x = o2; c.ldx = 256; c.y = br == 0 ? F0 : NN; c.ldy = 1;
-    RC(run_conv(r, c, tL));
+    const ConvW& pw = br == 0 ? e.f0_proj : e.n_proj;
+    static const bool proj_simt = getenv("TTSB_ROWDOT_SIMT") != nullptr;        // the tiled fp32 conv kernel: kept for bit-for-bit checks
+    if (!proj_simt && pw.k == 1 && pw.Cout == 1 && pw.Cin <= 512) {
+      r.e.prof.begin(r.s, PROF_CONV_SIMT, 2.0 * RL * pw.Cin, 4.0 * RL * (pw.Cin + 1.0));
+      CK(launch_rowdot(o2, 256, RL, pw.Cin, pw.w, pw.ldw, pw.bias, br == 0 ? F0 : NN, 1, r.s));
+      r.e.prof.end(r.s);
+    } else {
+      ConvCall c; c.w = &pw; c.x = o2; c.ldx = 256; c.y = br == 0 ? F0 : NN; c.ldy = 1;
+      RC(run_conv(r, c, tL));
+    }
   }
   RC(r.tap("F0", F0, RL, 1, 1));
   RC(r.tap("N", NN, RL, 1, 1));

@@ -305,6 +305,38 @@ def test_service_isolates_a_request_the_engine_refuses(checkpoint):
         assert solo.numel() == mine.numel() and snr_db(solo.cpu(), mine.cpu()) > 100.0
 
 
+def _dump_with_env(tmp_path, tag, extra_env):
+    """run tests/dump_source.py in a process of its own (the library reads its diagnostic switches once per process)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    for k in ("TTSB_PHASE_SERIAL", "TTSB_STYLE_SIMT", "TTSB_ROWDOT_SIMT"):
+        env.pop(k, None)
+    env.update(extra_env)
+    f = str(tmp_path / f"{tag}.pt")
+    subprocess.run([sys.executable, os.path.join(root, "tests", "dump_source.py"), f], check=True, env=env, cwd=root, timeout=300, stdout=subprocess.DEVNULL)
+    return torch.load(f)
+
+
+def test_style_projection_kernel_equals_tiled_conv(tmp_path):
+    """the style projection (128 -> all AdaIN / AdaLayerNorm scales and shifts of a style half, one row per utterance) has a kernel
+    of its own with the accumulation order of the tiled fp32 conv kernel it replaces: harmonic source and waveforms - everything
+    downstream of those scales and shifts, durations included - must be bit-identical between the two"""
+    new, old = _dump_with_env(tmp_path, "proj", {}), _dump_with_env(tmp_path, "tiled", {"TTSB_STYLE_SIMT": "1"})
+    for k in old:
+        assert old[k].shape == new[k].shape and torch.equal(old[k], new[k]), f"{k} differs between the style-projection kernel and the tiled conv"
+
+
+def test_f0_n_projection_kernel_equals_tiled_conv(tmp_path):
+    """F0_proj / N_proj (Conv1d(256, 1, 1) over every F0-rate row) as a row dot product with the tiled kernel's accumulation order:
+    F0 feeds the phase integrator, so any difference would show in the harmonic source and the waveforms - they are bit-identical"""
+    new, old = _dump_with_env(tmp_path, "rowdot", {}), _dump_with_env(tmp_path, "tiled", {"TTSB_ROWDOT_SIMT": "1"})
+    for k in old:
+        assert old[k].shape == new[k].shape and torch.equal(old[k], new[k]), f"{k} differs between the row-dot kernel and the tiled conv"
+
+
 def test_phase_scan_parallel_equals_serial(tmp_path):
     """the harmonic phase is an integrator: the warp-parallel prefix sum must give the SAME floats as the
     serial running sum of the reference order.  It does because the additions are exact in double (frame_kernels.cu); here both
