@@ -50,9 +50,11 @@ secs, ms = run(w["ids"], w["ref_s"], w["speeds"], reps=3, warm=1)
 print(f"| 3b | same 6 chunks as ONE batch | {secs:.1f} | {ms:.2f} | {secs / ms * 1e3:.0f} | what a frame-budgeted batcher would do |")
 # 4: vocoder sweep
 for B in (1, 16, 64):
-    for L in (100, 400, 1000, 4000):
+    for L in (100, 200, 400, 1000, 2000, 4000):           # the full grid
         if B * L > 64 * 1000:
-            continue                      # keep the workspace bounded (64 x 4000 would need > 100 GB of fp32 stage buffers)
+            # keep the workspace bounded (64 x 4000 would need > 100 GB of fp32 stage buffers): the cell is listed, not run
+            print(f"| 4 | vocoder only B={B} L={L} | {B * L * 300 / 24000.0:.1f} | - | - | not run: {B * L} generator frames exceed the 64 000-frame workspace bound of this sweep |")
+            continue
         x, s, f0, noise = vocoder_inputs(B, L)
         ms_l = []
         for i in range(4):
