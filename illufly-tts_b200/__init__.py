@@ -10,10 +10,10 @@ Layout
 
 There is no CPU fallback: importing works anywhere, creating an engine needs the built library and a B200.
 """
-from .engine import Engine, SynthesisResult, PRECISION_FP32, PRECISION_BF16, PRECISION_FP16  # noqa: F401
+from .engine import Engine, SynthesisResult, PRECISION_FP32, PRECISION_BF16, PRECISION_FP16, PRECISION_FP32_FFMA  # noqa: F401
 from .kmodel import BatchKModel, install_into_reference  # noqa: F401
 from .partition import lpt_partition, micro_batches  # noqa: F401
 from .service import ReferencePolicyManager, TaskStatus, TTSServiceManager, TTSTask  # noqa: F401
 
 __all__ = ["Engine", "SynthesisResult", "BatchKModel", "install_into_reference", "lpt_partition", "micro_batches", "TTSServiceManager", "ReferencePolicyManager", "TaskStatus", "TTSTask",
-           "PRECISION_FP32", "PRECISION_BF16", "PRECISION_FP16"]
+           "PRECISION_FP32", "PRECISION_BF16", "PRECISION_FP16", "PRECISION_FP32_FFMA"]

@@ -8,7 +8,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TTSB_LIB") or os.path.join(_HERE, "lib", "libttsb200.so")     # TTSB_LIB: A/B experiments only
 
-OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM, E_TOO_LONG = 0, -1, -2, -3, -4, -5
+OK, E_INVALID, E_CUDA, E_STATE, E_NOMEM, E_TOO_LONG, E_RANGE = 0, -1, -2, -3, -4, -5, -6
 MEM_HOST, MEM_DEVICE = 0, 1
 
 _p = C.c_void_p

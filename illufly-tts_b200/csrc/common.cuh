@@ -52,6 +52,9 @@ struct ConvArgs {
   double* ostats; int ld_ostats;       // [nseg][ld_ostats][2]
   const Seg* segs; const Tile* tiles; int ntiles; int tile_rows;
   uint8_t* xpack; size_t xpack_bytes;  // scratch for the pre-packed split-fp16 operand images of k=1 layers (conv_umma.cu), or null
+  int x_f16, y_f16;                    // conv_umma_wa.cu only: x / y point to fp16 rows (the c1 -> c2 intermediate of a resblock), ldx / ldy in elements
+  float split_wscale;                  // wfmt 2: the power of two the weights of this layer were scaled by at pack time
+  unsigned int* sat;                   // wfmt 2: device counter of operand conversions that left fp16's range (|16 x| > 65504), or null
 };
 
 struct LstmSeg {                       // host-side description of one utterance's recurrence
@@ -78,6 +81,11 @@ cudaError_t launch_style_proj(const float* style, int ld_style, int nseg, const 
                               int N, cudaStream_t s);   // out[b][n] = bias[n] + sum_k style[b][k] w[k][n], a few rows b
 cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s);     // tcgen05 bf16 path (k*dil halo, Cin%16==0 after padding)
 bool conv_umma_supported(const ConvArgs& a);
+// tcgen05 path with the WEIGHTS as the A operand (M = Cout = 128 TMEM lanes, N = 256 time rows): the 128-channel layers
+// (conv_umma_wa.cu).  tile_rows of the tile table must be CONV_WA_TILE_ROWS.
+constexpr int CONV_WA_TILE_ROWS = 256;
+cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s);
+bool conv_umma_wa_supported(const ConvArgs& a);
 
 cudaError_t launch_lstm_cluster(const float* gx, const float* whh, const float* bias, float* y, int ldy, const LstmGroup* groups, int ngroups,
                                 cudaStream_t s);
@@ -110,7 +118,7 @@ cudaError_t launch_source_stft(const float* f0, const float* noise, const float*
                                cudaStream_t s);
 cudaError_t launch_up_add(const float* up, int ldu, int up_row_shift, int reflect, const float* xs, int ldxs, float* y, int ldy, int C,
                           const Seg* segs, int nseg, int max_out_len, double* ostats, int ld_ostats, cudaStream_t s);
-cudaError_t launch_istft(const float* cp, int ld, float* audio, const Seg* segs, int nseg, int max_frames, cudaStream_t s);
+cudaError_t launch_istft(const float* cp, int ld, float* audio, const Seg* segs, int nseg, int max_frames, bool precise, cudaStream_t s);
 cudaError_t launch_adain_snake(const float* x, int ldx, float* y, int ldy, int C, const double* pstats, int ld_pstats, const float* gb, int ld_gb,
                                int beta_off, const float* alpha, const Seg* segs, int nseg, int max_len, cudaStream_t s);
 cudaError_t launch_zero_f64(double* p, size_t n, cudaStream_t s);
@@ -144,6 +152,8 @@ __device__ __forceinline__ void adain_coef(const double* st, int n, float gamma,
 #include <vector>
 namespace ttsb {
 // host: repack fp32 [k][Cin][ldw] weights into the bf16 shared-memory image the tcgen05 kernel streams (conv_umma.cu)
-void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fmt, std::vector<uint16_t>& out, int& cin_pad, int& cout_pad);
+// split_scale (fmt 2 only): receives the per-layer power-of-two weight scale (ConvArgs::split_wscale)
+void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fmt, std::vector<uint16_t>& out, int& cin_pad, int& cout_pad,
+                       float* split_scale = nullptr);
 const char* last_error();
 }  // namespace ttsb

@@ -18,6 +18,7 @@
 //   squares for the NEXT AdaIN, so InstanceNorm never costs a pass of its own.
 // Reference maths: SURVEY.md A.7, A.11, A.12 (kokoro AdainResBlk1d / Generator / AdaINResBlock1).
 #include "common.cuh"
+#include "umma_ptx.cuh"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,6 +26,8 @@
 #include <algorithm>
 
 namespace ttsb {
+
+using namespace umma;
 
 namespace {
 
@@ -37,10 +40,14 @@ constexpr int NTHREADS = NPROD + 64 + NEPI + 32;   // producers (0-7), weight lo
 constexpr int MAXRAW = 8;               // slots of the raw-row ring
 constexpr int MAXSTAGE = 8;
 // split-fp16 mode: operands are pre-scaled by powers of two so that the low halves stay in fp16's normal range
-constexpr float SPLIT_SA = 16.f, SPLIT_SW = 256.f;
+// (activations by a fixed 16: |x| > 4094 would saturate and is counted in ConvArgs::sat; weights by a per-layer power of two chosen
+// at pack time from max|w|, ConvArgs::split_wscale)
+constexpr float SPLIT_SA = 16.f;
+// Snake's cosine: the fast intrinsic in the 16-bit operand modes (its 2^-21 absolute error is far below the operand rounding),
+// the accurate one in the split-fp16 (fp32-class) mode
+template <int WFMT> __device__ __forceinline__ float snake_cos(float t) { return WFMT == 2 ? cosf(t) : __cosf(t); }
 constexpr int STG_LD = 36;              // floats per staging row (32 + 4 pad: 16-B aligned rows, conflict-free both ways)
 constexpr int STG_BYTES = 32 * STG_LD * 4;
-constexpr uint32_t SPIN_LIMIT = 40u * 1000u * 1000u;
 
 struct Plan {
   int BN, KS, nsc, SR, kcn, tmem_cols, ntile_n, nstage, items, per_cta, split, acc_cols;
@@ -56,103 +63,6 @@ struct UArgs {
   int dbg;     // TTSB_UMMA_DBG (timing experiments only, results become garbage): 1 = producers skip global loads,
                // 2 = epilogue skips global traffic, 4 = no MMA issue; applied to the Snake-prologue variants only
 };
-
-// ---- PTX wrappers --------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > SPIN_LIMIT) __trap();
-  }
-}
-// timed variant for the role profile (cycles spent waiting are added to *acc)
-__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long& acc) {
-  const long long t0 = clock64();
-  mbar_wait(bar, parity);
-  acc += clock64() - t0;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc),
-      "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
-        "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-// shared-memory operand descriptor, K-major, no swizzle (layout_type 0), version 1 (Blackwell):
-//   core matrix = 8 rows x 16 B contiguous; LBO = byte distance between the two 16-B K chunks of one K=16 MMA,
-//   SBO = byte distance between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ uint32_t pack_f16_nosat(float lo, float hi) {
-  __half2 t = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  lo = fminf(fmaxf(lo, -65504.f), 65504.f);     // saturate instead of producing inf
-  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-  __half2 t = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-
 
 // One 32-row x 32-column chunk of the epilogue for a warp, fast path: the tile is fully inside the utterance, the channel
 // group is complete, no activation.  y = (acc * acs + bias [+ res]) [* os] [+ y_old]; returns the lane's partial column sums.
@@ -261,6 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     const int pln = tid % planes, r0 = tid / planes;
     int cur_seg = -1, par_c0 = -1, par_seg = -1;
     float pA[8], pB[8], pA2[8], pB2[8], pK[8];
+    float satm = 0.f;                                  // split mode: largest |operand| this thread converted (range check, ConvArgs::sat)
     uint32_t g = 0;                                    // running slab counter of this CTA
     uint32_t rslot = 0, rphase = 0;                    // position in the raw-row ring
     long long t_wait = 0;
@@ -338,7 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
                 float x = v[h][e];
                 if (PRO == PRO_LRELU) x = fmaxf(x, x * p.slope);                    // slope < 1
                 else if (PRO == PRO_ADAIN_LRELU) { const float wv = fmaf(x, pA[e], pB[e]); x = fmaxf(wv, wv * p.slope); }
-                else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-pK[e], __cosf(fmaf(x, pA2[e], pB2[e])), fmaf(x, pA[e], pB[e]));
+                else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-pK[e], snake_cos<WFMT>(fmaf(x, pA2[e], pB2[e])), fmaf(x, pA[e], pB[e]));
                 v[h][e] = x;
               }
               if (tailc) {
@@ -352,6 +263,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
               float hi[8], lo[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
+                satm = fmaxf(satm, fabsf(v[h][e]));
                 const float xs = fminf(fmaxf(v[h][e] * SPLIT_SA, -65504.f), 65504.f);
                 hi[e] = __half2float(__float2half_rn(xs));
                 lo[e] = xs - hi[e];                        // exact in fp32; its own fp16 rounding error is ~2^-22 of x
@@ -382,7 +294,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             float x = v[e];
             if (PRO == PRO_LRELU) x = fmaxf(x, x * p.slope);
             else if (PRO == PRO_ADAIN_LRELU) { const float wv = fmaf(x, pA[e], pB[e]); x = fmaxf(wv, wv * p.slope); }
-            else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-pK[e], __cosf(fmaf(x, pA2[e], pB2[e])), fmaf(x, pA[e], pB[e]));
+            else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-pK[e], snake_cos<WFMT>(fmaf(x, pA2[e], pB2[e])), fmaf(x, pA[e], pB[e]));
             v[e] = x;
           }
           uint4 o;
@@ -391,6 +303,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             float hi[8], lo[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
+              satm = fmaxf(satm, fabsf(v[e]));
               const float xs = fminf(fmaxf(v[e] * SPLIT_SA, -65504.f), 65504.f);
               hi[e] = __half2float(__float2half_rn(xs));
               lo[e] = xs - hi[e];
@@ -476,6 +389,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         mbar_arrive(bar_slab_full(b));
       }
     }
+    if (WFMT == 2 && p.sat && satm * SPLIT_SA > 65504.f) atomicAdd(p.sat, 1u);
     if (u.prof && tid == 0) { u.prof[blockIdx.x * 16 + 0] = clock64() - t_start; u.prof[blockIdx.x * 16 + 1] = t_wait; }
   } else if (warp == NPW) {
     // =================== weight loader (bulk-copy engine) ===================
@@ -821,7 +735,7 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const ConvArgs p, int KS,
         const int cl = pln * 8 + e;
         if (PRO == PRO_LRELU) x = fmaxf(x, x * p.slope);
         else if (PRO == PRO_ADAIN_LRELU) { const float wv = fmaf(x, s_par[0][cl], s_par[1][cl]); x = fmaxf(wv, wv * p.slope); }
-        else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-s_par[4][cl], __cosf(fmaf(x, s_par[2][cl], s_par[3][cl])), fmaf(x, s_par[0][cl], s_par[1][cl]));
+        else if (PRO == PRO_ADAIN_SNAKE) x = fmaf(-s_par[4][cl], snake_cos<WFMT>(fmaf(x, s_par[2][cl], s_par[3][cl])), fmaf(x, s_par[0][cl], s_par[1][cl]));
         v[e] = (c0 + e < p.Cin) ? x : 0.f;
       }
     }
@@ -829,11 +743,15 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const ConvArgs p, int KS,
     if (WFMT == 2) {
       float hi[8], lo[8];
 #pragma unroll
+      float satm = 0.f;
+#pragma unroll
       for (int e = 0; e < 8; ++e) {
+        satm = fmaxf(satm, fabsf(v[e]));
         const float xs = fminf(fmaxf(v[e] * SPLIT_SA, -65504.f), 65504.f);
         hi[e] = __half2float(__float2half_rn(xs));
         lo[e] = xs - hi[e];
       }
+      if (p.sat && satm * SPLIT_SA > 65504.f) atomicAdd(p.sat, 1u);
       uint4 ol;
       o.x = pack_f16_nosat(hi[0], hi[1]); o.y = pack_f16_nosat(hi[2], hi[3]); o.z = pack_f16_nosat(hi[4], hi[5]); o.w = pack_f16_nosat(hi[6], hi[7]);
       ol.x = pack_f16_nosat(lo[0], lo[1]); ol.y = pack_f16_nosat(lo[2], lo[3]); ol.z = pack_f16_nosat(lo[4], lo[5]); ol.w = pack_f16_nosat(lo[6], lo[7]);
@@ -915,10 +833,25 @@ bool make_plan(const ConvArgs& a, Plan& pl) {
 }  // namespace
 
 // 16-bit (bf16 or fp16) image of the weights: [Cout tile][tap][64-channel chunk][8-channel plane][BN rows][8 channels]
-void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fmt, std::vector<uint16_t>& out, int& cin_pad, int& cout_pad) {
+void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fmt, std::vector<uint16_t>& out, int& cin_pad, int& cout_pad,
+                       float* split_scale) {
   int BN;
   const bool split = fmt == 2;
   pads(Cin, Cout, split, cin_pad, cout_pad, BN);
+  // split mode: the largest power of two that keeps max|w| * scale <= 2^14 (fp16 overflows at 65504; the headroom is for the
+  // rounding of the high half), so that the low halves sit as high in fp16's range as the layer allows.  A fixed 256 turned
+  // |w| >= 256 into inf and then NaN.
+  float SPLIT_SW = 256.f;
+  if (split) {
+    float mx = 0.f;
+    for (int j = 0; j < k; ++j)
+      for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co) mx = std::max(mx, fabsf(w[((size_t)j * Cin + ci) * ldw + co]));
+    int ex = 12;
+    while (ex > -14 && !(mx * ldexpf(1.f, ex) <= 16384.f)) --ex;      // also walks down for inf / NaN weights (the pack is then garbage either way)
+    SPLIT_SW = ldexpf(1.f, ex);
+  }
+  if (split_scale) *split_scale = SPLIT_SW;
   const int kcn = cin_pad / KCH, ntn = cout_pad / BN;
   const size_t blk = (size_t)BN * KCH * (split ? 2 : 1);          // one stage: [hi block][lo block] in split mode
   out.assign((size_t)ntn * k * kcn * blk, (uint16_t)0);
@@ -964,7 +897,10 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   UArgs u;
   u.a = a;
   if (!make_plan(a, u.p)) return cudaErrorInvalidValue;
-  if (a.wfmt == 2) u.a.acc_scale = 1.0f / (SPLIT_SA * SPLIT_SW);
+  if (a.wfmt == 2) {
+    if (!(a.split_wscale > 0.f)) return cudaErrorInvalidValue;
+    u.a.acc_scale = 1.0f / (SPLIT_SA * a.split_wscale);
+  }
   using KernelFn = void (*)(const UArgs);
   static const KernelFn table[4][3] = {
       {conv_umma_kernel<PRO_NONE, 0>, conv_umma_kernel<PRO_NONE, 1>, conv_umma_kernel<PRO_NONE, 2>},

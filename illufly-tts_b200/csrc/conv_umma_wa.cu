@@ -1,0 +1,507 @@
+// tcgen05 implicit-GEMM Conv1d for the 128-channel layers (stage 1 of the generator: 24 of the 48 resblock convs, 46 % of the
+// conv time of a step), with the WEIGHTS as the A operand:
+//
+//   D[Cout (M = 128 TMEM lanes), time (N = 256 TMEM columns)] += W[tap][Cout, Cin chunk] * X[time + tap*dil - pad, Cin chunk]^T
+//
+// Why the roles are swapped relative to conv_umma.cu.  There the time axis is M (128 rows) and Cout is N; for Cout = 128 an
+// M128 x N128 x K16 MMA lasts 64 tensor cycles and reads 4 KB of A and 4 KB of B from shared memory: 128 B/clk, the SM's whole
+// shared-memory bandwidth, before the producers, the weight stream and the epilogue staging get any (ncu, round 1:
+// sm__pipe_tensor_cycles_active 13-41 % on these layers).  With the weights as A and 256 time rows as N the MMA lasts 128
+// cycles for 4 KB + 8 KB = 96 B/clk, the 360-KB weight stream of a k11 layer is re-read once per 256 rows instead of once per
+// 128, the halo rows of a slab are 16 % of it instead of 28 %, and the accumulator comes out channel-per-lane: a thread of
+// the epilogue owns ONE output channel, so
+//   * a warp's store of one time step is 32 consecutive floats (one 128-B line) straight from registers - no shared-memory
+//     staging tile, no bank conflicts;
+//   * bias is one register, and the per-(utterance, channel) sum / sum of squares for the next AdaIN are per-thread running
+//     sums - no shuffles, no shared-memory statistics, one pair of double atomics per thread when the utterance changes.
+// The c1 -> c2 intermediate of an AdaINResBlock1 (SURVEY.md A.12 `xt`) is only ever consumed as a 16-bit operand: this kernel
+// can write it as fp16 (y_f16) and read it back as fp16 (x_f16), halving its HBM traffic and the raw-row ring's.
+//
+// Same machinery as conv_umma.cu otherwise: persistent CTAs (one per SM, contiguous tile ranges), warp-specialised roles
+// (8 producer warps, weight loader, MMA issuer, 8 epilogue warps, row loader = 608 threads), two operand slabs, a raw-row ring
+// fed by the bulk-copy engine, an mbarrier ring of weight stages, two TMEM accumulators (2 x 256 columns = all of TMEM).
+// Operand layouts: no-swizzle K-major [8-channel plane][row][16 B] for both; a tap is a row offset of the B descriptor.
+// Fused prologue: InstanceNorm normalise + AdaIN affine + Snake (PRO_ADAIN_SNAKE), as conv_umma.cu.
+#include "common.cuh"
+#include "umma_ptx.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+namespace ttsb {
+
+using namespace umma;
+
+namespace {
+
+constexpr int TN = CONV_WA_TILE_ROWS;   // time rows per tile = N of the MMA
+constexpr int CH = 128;                 // Cin = Cout
+constexpr int KCH = 64;                 // channels per weight stage
+constexpr int PLANES = CH / 8;          // 8-channel planes of a slab
+constexpr int NPROD = 256;              // 8 producer warps
+constexpr int RPP = NPROD / PLANES;     // slab rows the producers cover per pass (16)
+constexpr int NEPI = 256;               // 8 epilogue warps: two per TMEM lane quadrant, 128 columns each
+constexpr int NTHREADS = NPROD + 64 + NEPI + 32;   // producers (0-7), weight loader (8), MMA issuer (9), epilogue (10-17), row loader (18)
+constexpr int MAXRAW = 8;
+constexpr int MAXSTAGE = 6;
+constexpr uint32_t WSTAGE_BYTES = CH * KCH * 2;    // one (tap, 64-channel) weight stage: 16 KB
+
+struct WPlan {
+  int SR;                               // slab rows: TN + (k-1) dil, made odd (conflict-free 16-B stores across planes)
+  int nstage, nraw, rps, rch, nch;      // weight stages; ring slots, rows per producer thread per slot, rows per slot, slots per slab
+  int items, per_cta;
+  uint32_t off_bar, off_par, off_slab, slab_bytes, off_raw, raw_bytes, off_w, smem_bytes, row_bytes;
+};
+
+struct WArgs {
+  ConvArgs a;
+  WPlan p;
+  long long* prof;
+};
+
+// eight rows of one 32-column chunk: y[row0 + i][c] for i = I0 .. I0+7, one output channel c per thread
+template <bool RES, bool SCALE, bool ACC, bool YH>
+__device__ __forceinline__ void epi_rows8(const uint32_t (&v)[32], const int i0, const int nvalid, const float bias, const float os, float* __restrict__ yb,
+                                          __half* __restrict__ yh, const size_t ldy, const float* __restrict__ rb, const size_t ldr, float& ps, float& pq) {
+  float r[8], yo[8];
+  if (RES) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = (i0 + i < nvalid) ? rb[(size_t)(i0 + i) * ldr] : 0.f;
+  }
+  if (ACC) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yo[i] = (i0 + i < nvalid) ? yb[(size_t)(i0 + i) * ldy] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i0 + i < nvalid) {
+      float o = __uint_as_float(v[i0 + i]) + bias;
+      if (RES) o += r[i];
+      if (SCALE && ACC) o = fmaf(o, os, yo[i]);
+      else if (SCALE) o *= os;
+      else if (ACC) o += yo[i];
+      if (YH) {
+        const __half h = __float2half_rn(fminf(fmaxf(o, -65504.f), 65504.f));
+        yh[(size_t)(i0 + i) * ldy] = h;
+        o = __half2float(h);                      // the statistics describe what the consumer will read
+      } else {
+        yb[(size_t)(i0 + i) * ldy] = o;
+      }
+      ps += o;
+      pq = fmaf(o, o, pq);
+    }
+  }
+}
+
+template <int WFMT, bool XH, bool YH>
+__global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const ConvArgs& p = u.a;
+  const WPlan& pl = u.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = pl.nstage;
+
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
+  const uint32_t bar0 = smem_u32(smem + pl.off_bar);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (MAXSTAGE + s); };
+  auto bar_slab_full = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + b); };
+  auto bar_slab_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 2 + b); };
+  auto bar_acc_full = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 4 + b); };
+  auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 6 + b); };
+  auto bar_raw_full = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 8 + b); };
+  auto bar_raw_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 8 + MAXRAW + b); };
+  float* s_par = reinterpret_cast<float*>(smem + pl.off_par);       // [5][CH]: A, B (+k), 2 alpha A, 2 alpha B, k
+
+  const int item0 = blockIdx.x * pl.per_cta;
+  const int item1 = min(item0 + pl.per_cta, pl.items);
+
+  // ---- one-time setup ----
+  if (warp == 9) tmem_alloc(smem_u32(s_tmem), 512u);
+  if (tid == 0) {
+    for (int s = 0; s < MAXSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_slab_full(b), NPROD); mbar_init(bar_slab_empty(b), 1);
+      mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), NEPI);
+    }
+    for (int b = 0; b < MAXRAW; ++b) { mbar_init(bar_raw_full(b), 1); mbar_init(bar_raw_empty(b), NPROD); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const uint32_t slab0 = smem_u32(smem + pl.off_slab);
+  const uint32_t w0 = smem_u32(smem + pl.off_w);
+  const int SR = pl.SR;
+  constexpr int ESZ = XH ? 2 : 4;
+  const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
+
+  if (warp < 8) {
+    // =================== producers: raw rows -> AdaIN + Snake -> 16-bit operand slab ===================
+    const int pln = tid & (PLANES - 1), r0 = tid >> 4;
+    const int c0 = pln * 8;
+    float pA[8], pB[8], pA2[8], pB2[8], pK[8];
+    int cur_seg = -1;
+    uint32_t rslot = 0, rphase = 0, n = 0;
+    long long t_wait = 0;
+    const long long t_start = clock64();
+    auto xform_store = [&](uint8_t* slab, int rr, float (&v)[8]) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaf(-pK[e], __cosf(fmaf(v[e], pA2[e], pB2[e])), fmaf(v[e], pA[e], pB[e]));
+      uint4 o;
+      // instance-normalised data is bounded (|x^| <= sqrt(n)): no saturation needed for fp16
+      if (WFMT == 1) { o.x = pack_f16_nosat(v[0], v[1]); o.y = pack_f16_nosat(v[2], v[3]); o.z = pack_f16_nosat(v[4], v[5]); o.w = pack_f16_nosat(v[6], v[7]); }
+      else { o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]); }
+      *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = o;
+    };
+    auto unpack_h8 = [](const uint4 q, float (&v)[8]) {
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+    };
+    for (int item = item0; item < item1; ++item, ++n) {
+      const Tile tile = p.tiles[item];
+      const Seg seg = p.segs[tile.seg];
+      if (tile.seg != cur_seg) {
+        // per-(utterance, channel) AdaIN coefficients; only producers read them, so a producer-only barrier suffices
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+        if (tid < CH) {
+          const int c = tid;
+          float mean, a, b;
+          const double* st = p.pstats + ((size_t)tile.seg * p.ld_pstats + c) * 2;
+          adain_coef(st, seg.in_len, p.gb[(size_t)tile.seg * p.ld_gb + c], p.gb[(size_t)tile.seg * p.ld_gb + p.beta_off + c], mean, a, b);
+          const float al = p.alpha[c];
+          // AdaIN is one FFMA  w = x A + B  (A = (1+gamma) rstd, B = beta - mean A); Snake  w + sin^2(alpha w)/alpha =
+          // (w + k) - k cos(2 alpha w),  k = 1/(2 alpha):  wk = x A + (B + k),  t = x (2 alpha A) + 2 alpha B
+          const float Bf = fmaf(-mean, a, b);
+          const float kk = 0.5f / al;
+          s_par[c] = a; s_par[CH + c] = Bf + kk; s_par[2 * CH + c] = 2.f * al * a; s_par[3 * CH + c] = 2.f * al * Bf; s_par[4 * CH + c] = kk;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pA[e] = s_par[c0 + e]; pB[e] = s_par[CH + c0 + e]; pA2[e] = s_par[2 * CH + c0 + e]; pB2[e] = s_par[3 * CH + c0 + e]; pK[e] = s_par[4 * CH + c0 + e];
+        }
+        cur_seg = tile.seg;
+      }
+      const uint32_t b = n & 1u;
+      mbar_wait_t(bar_slab_empty(b), ((n >> 1) & 1u) ^ 1u, t_wait);
+      uint8_t* slab = smem + pl.off_slab + (size_t)b * pl.slab_bytes + (size_t)pln * SR * 16;
+      const int row_lo = tile.t0 - p.pad;
+      if (pl.nraw > 0 && row_lo >= 0 && row_lo + SR <= seg.in_len) {
+        // interior tile: the row loader streams the raw rows through the ring with the bulk-copy engine
+        for (int ch = 0; ch < pl.nch; ++ch) {
+          mbar_wait_t(bar_raw_full(rslot), rphase, t_wait);
+          const uint8_t* slot = smem + pl.off_raw + (size_t)rslot * pl.raw_bytes;
+          const int ra = ch * pl.rch + r0, rb = ra + RPP;
+          const bool hasa = ra < SR, hasb = pl.rps > 1 && rb < SR;
+          float va[8], vb[8];
+          if (XH) {
+            const uint4 qa = *reinterpret_cast<const uint4*>(slot + (size_t)(r0 * CH + c0) * 2);
+            const uint4 qb = *reinterpret_cast<const uint4*>(slot + (size_t)((hasb ? r0 + RPP : r0) * CH + c0) * 2);
+            unpack_h8(qa, va); unpack_h8(qb, vb);
+          } else {
+            // groups of four lanes alternate which 16-B half of their 32 B they read first: eight lanes x 16 B at a 32-B
+            // stride would hit every bank group twice
+            const int hf = (tid >> 2) & 1;
+            const float* sa = reinterpret_cast<const float*>(slot) + r0 * CH + c0;
+            const float* sb = hasb ? sa + RPP * CH : sa;
+            const float4 ax = *reinterpret_cast<const float4*>(sa + 4 * hf), ay = *reinterpret_cast<const float4*>(sa + 4 * (hf ^ 1));
+            const float4 bx = *reinterpret_cast<const float4*>(sb + 4 * hf), by = *reinterpret_cast<const float4*>(sb + 4 * (hf ^ 1));
+            const float4 a0 = hf ? ay : ax, a1 = hf ? ax : ay, b0 = hf ? by : bx, b1 = hf ? bx : by;
+            va[0] = a0.x; va[1] = a0.y; va[2] = a0.z; va[3] = a0.w; va[4] = a1.x; va[5] = a1.y; va[6] = a1.z; va[7] = a1.w;
+            vb[0] = b0.x; vb[1] = b0.y; vb[2] = b0.z; vb[3] = b0.w; vb[4] = b1.x; vb[5] = b1.y; vb[6] = b1.z; vb[7] = b1.w;
+          }
+          if (hasa) xform_store(slab, ra, va);
+          if (hasb) xform_store(slab, rb, vb);
+          mbar_arrive(bar_raw_empty(rslot));      // this thread is done reading the slot
+          if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
+        }
+      } else {
+        // edge tile of an utterance (or no ring): rows outside the utterance are zero AFTER the activation, as torch pads
+        for (int rr = r0; rr < SR; rr += RPP) {
+          const int tin = row_lo + rr;
+          float v[8];
+          if (tin >= 0 && tin < seg.in_len) {
+            const uint8_t* src = xbytes + ((size_t)(seg.in_off + tin) * p.ldx + c0) * ESZ;
+            if (XH) unpack_h8(__ldg(reinterpret_cast<const uint4*>(src)), v);
+            else {
+              const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+              v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+            }
+            xform_store(slab, rr, v);
+          } else {
+            *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+      fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
+      mbar_arrive(bar_slab_full(b));
+    }
+    if (u.prof && tid == 0) { u.prof[blockIdx.x * 16 + 0] = clock64() - t_start; u.prof[blockIdx.x * 16 + 1] = t_wait; }
+  } else if (warp == 8) {
+    // =================== weight loader (bulk-copy engine) ===================
+    if (lane == 0) {
+      uint32_t it = 0;
+      const int nblk = p.k * (CH / KCH);                 // stages per tile, in pack order [tap][64-channel chunk]
+      for (int item = item0; item < item1; ++item)
+        for (int blk = 0; blk < nblk; ++blk, ++it) {
+          const uint32_t s = it % NS;
+          mbar_wait(bar_empty(s), ((it / NS) & 1u) ^ 1u);
+          mbar_expect_tx(bar_full(s), WSTAGE_BYTES);
+          bulk_g2s(w0 + s * WSTAGE_BYTES, p.wb + (size_t)blk * (WSTAGE_BYTES / 2), WSTAGE_BYTES, bar_full(s));
+        }
+    }
+  } else if (warp == 9) {
+    // =================== MMA issuer ===================
+    // the whole warp walks the loops with warp-uniform values (descriptors live in uniform registers); one elected lane issues
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(leader));
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t ofmt = WFMT >= 1 ? 0u : 1u;       // operand format: 0 = F16, 1 = BF16
+    const uint32_t idesc = (1u << 4) | (ofmt << 7) | (ofmt << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(CH >> 4) << 24);
+    // A = weights [8-ch plane][128 Cout rows][16 B]: LBO (between the two K chunks of a K16 step) = 128 * 16, SBO (8-row groups) = 128
+    // B = slab    [8-ch plane][SR rows][16 B]:       LBO = SR * 16, SBO = 128; a tap is a row offset of the start address
+    const uint64_t a_desc0 = make_desc(0, (uint32_t)CH * 16u, 128u), b_desc0 = make_desc(0, (uint32_t)SR * 16u, 128u);
+    const uint32_t a_kstep = 2u * CH;                  // two planes per K16 step, in 16-B units
+    const uint32_t b_kstep = 2u * (uint32_t)SR;
+    uint32_t it = 0, n = 0;
+    long long tw_slab = 0, tw_acc = 0, tw_w = 0;
+    const long long t_start = clock64();
+    for (int item = item0; item < item1; ++item, ++n) {
+      const uint32_t slot = n & 1u;
+      mbar_wait_t(bar_acc_empty(slot), ((n >> 1) & 1u) ^ 1u, tw_acc);       // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tacc = tmem_u + slot * (uint32_t)TN;
+      mbar_wait_t(bar_slab_full(slot), (n >> 1) & 1u, tw_slab);
+      tc_fence_after();
+      const uint32_t sbase = slab0 + slot * pl.slab_bytes;
+      uint32_t first = 1;
+      for (int j = 0; j < p.k; ++j)
+        for (int kc = 0; kc < CH / KCH; ++kc, ++it) {
+          const uint32_t s = it % NS;
+          mbar_wait_t(bar_full(s), (it / NS) & 1u, tw_w);
+          tc_fence_after();
+          const uint64_t ad0 = a_desc0 + (uint64_t)((w0 + s * WSTAGE_BYTES) >> 4);
+          const uint64_t bd0 = b_desc0 + (uint64_t)((sbase >> 4) + (uint32_t)(kc * 8 * SR + j * p.dil));
+#pragma unroll
+          for (int kk = 0; kk < KCH / 16; ++kk) {
+            if (leader) umma_bf16(tacc, ad0 + (uint64_t)(kk * a_kstep), bd0 + (uint64_t)(kk * b_kstep), idesc, first ? 0u : 1u);
+            first = 0;
+          }
+          if (leader) umma_commit(bar_empty(s));            // weight stage free once these MMAs have read it
+          __syncwarp();
+        }
+      if (leader) umma_commit(bar_slab_empty(slot));        // slab free once every MMA issued so far has completed
+      if (leader) umma_commit(bar_acc_full(slot));          // accumulator of this item complete
+      __syncwarp();
+    }
+    if (u.prof && lane == 0) {
+      long long* pp = u.prof + blockIdx.x * 16;
+      pp[2] = clock64() - t_start; pp[3] = tw_slab; pp[4] = tw_acc; pp[5] = tw_w;
+    }
+  } else if (warp == 18) {
+    // =================== row loader: raw activation rows -> ring (bulk-copy engine) ===================
+    if (pl.nraw > 0 && lane == 0) {
+      uint32_t rslot = 0, rphase = 0;
+      for (int item = item0; item < item1; ++item) {
+        const Tile tile = p.tiles[item];
+        const Seg seg = p.segs[tile.seg];
+        const int row_lo = tile.t0 - p.pad;
+        if (!(row_lo >= 0 && row_lo + SR <= seg.in_len)) continue;      // edge tile: the producers load it themselves
+        for (int ch = 0; ch < pl.nch; ++ch) {
+          mbar_wait(bar_raw_empty(rslot), rphase ^ 1u);
+          const int rows_n = min(pl.rch, SR - ch * pl.rch);
+          const uint8_t* src = xbytes + (size_t)(seg.in_off + row_lo + ch * pl.rch) * pl.row_bytes;      // ldx == CH: rows are contiguous
+          const uint32_t bytes = (uint32_t)rows_n * pl.row_bytes;
+          mbar_expect_tx(bar_raw_full(rslot), bytes);
+          bulk_g2s(smem_u32(smem + pl.off_raw + (size_t)rslot * pl.raw_bytes), src, bytes, bar_raw_full(rslot));
+          if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // =================== epilogue: 8 warps, TMEM lane quadrant q = warp % 4, columns [128 half, 128 half + 128) ===================
+    const int q = warp & 3;
+    const int half = (warp - 10) >> 2;
+    const int c = q * 32 + lane;                       // this thread's output channel
+    const float bias = p.bias ? p.bias[c] : 0.f;
+    const bool has_res = p.res != nullptr, acc = p.accumulate != 0, sc = p.out_scale != 1.0f;
+    const size_t ldy = (size_t)p.ldy, ldr = (size_t)p.ldr;
+    double dsum = 0.0, dsq = 0.0;
+    uint32_t n = 0;
+    long long tw_full = 0;
+    const long long t_start = clock64();
+    for (int item = item0; item < item1; ++item, ++n) {
+      const Tile tile = p.tiles[item];
+      const Seg seg = p.segs[tile.seg];
+      const uint32_t slot = n & 1u;
+      mbar_wait_t(bar_acc_full(slot), (n >> 1) & 1u, tw_full);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + slot * (uint32_t)TN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+      const int tbase = tile.t0 + half * 128;
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(tacc + (uint32_t)(chunk * 32), v);
+        if (chunk == 3) {                              // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(bar_acc_empty(slot));
+        }
+        const int t0c = tbase + chunk * 32;
+        const int nvalid = min(32, seg.out_len - t0c);
+        if (nvalid > 0) {
+          const size_t row0 = (size_t)(seg.out_off + t0c);
+          float* yb = YH ? nullptr : p.y + row0 * ldy + c;
+          __half* yh = YH ? reinterpret_cast<__half*>(p.y) + row0 * ldy + c : nullptr;
+          const float* rb = has_res ? p.res + row0 * ldr + c : nullptr;
+          float ps = 0.f, pq = 0.f;
+#pragma unroll
+          for (int i0 = 0; i0 < 32; i0 += 8) {
+            if (YH) epi_rows8<false, false, false, true>(v, i0, nvalid, bias, 1.f, yb, yh, ldy, rb, ldr, ps, pq);
+            else if (has_res && acc) epi_rows8<true, true, true, false>(v, i0, nvalid, bias, p.out_scale, yb, yh, ldy, rb, ldr, ps, pq);
+            else if (has_res && sc) epi_rows8<true, true, false, false>(v, i0, nvalid, bias, p.out_scale, yb, yh, ldy, rb, ldr, ps, pq);
+            else if (has_res) epi_rows8<true, false, false, false>(v, i0, nvalid, bias, 1.f, yb, yh, ldy, rb, ldr, ps, pq);
+            else if (acc) epi_rows8<false, true, true, false>(v, i0, nvalid, bias, p.out_scale, yb, yh, ldy, rb, ldr, ps, pq);
+            else if (sc) epi_rows8<false, true, false, false>(v, i0, nvalid, bias, p.out_scale, yb, yh, ldy, rb, ldr, ps, pq);
+            else epi_rows8<false, false, false, false>(v, i0, nvalid, bias, 1.f, yb, yh, ldy, rb, ldr, ps, pq);
+          }
+          dsum += (double)ps; dsq += (double)pq;
+        }
+      }
+      if (p.ostats) {
+        // flush this thread's running sums when the utterance changes or the CTA is done
+        const bool flush = item + 1 >= item1 || p.tiles[item + 1].seg != tile.seg;
+        if (flush) {
+          double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + c) * 2;
+          atomicAdd(st, dsum);
+          atomicAdd(st + 1, dsq);
+          dsum = 0.0; dsq = 0.0;
+        }
+      }
+    }
+    tc_fence_before();
+    if (u.prof && tid == NPROD + 64) { u.prof[blockIdx.x * 16 + 6] = clock64() - t_start; u.prof[blockIdx.x * 16 + 7] = tw_full; u.prof[blockIdx.x * 16 + 8] = item1 - item0; }
+  }
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512u);
+}
+
+bool make_wplan(const ConvArgs& a, WPlan& pl) {
+  if (a.Cin != CH || a.Cout != CH || a.cin_pad != CH || a.cout_pad != CH) return false;
+  pl.SR = (TN + (a.k - 1) * a.dil) | 1;
+  pl.row_bytes = (uint32_t)CH * (a.x_f16 ? 2u : 4u);
+  uint32_t off = 16;
+  pl.off_bar = off; off += 8u * (2 * MAXSTAGE + 8 + 2 * MAXRAW);
+  off = (off + 15u) & ~15u;
+  pl.off_par = off; off += 5u * CH * 4u;
+  off = (off + 127u) & ~127u;
+  pl.off_slab = off;
+  pl.slab_bytes = ((uint32_t)PLANES * pl.SR * 16u + 127u) & ~127u;
+  off += 2 * pl.slab_bytes;
+  const uint32_t limit = 227u * 1024u;
+  // three weight stages (3 x 4 MMAs x 128 cycles of cover for one L2 round trip), then the ring, then more weight stages
+  pl.nstage = 3;
+  if (off + pl.nstage * WSTAGE_BYTES > limit) return false;
+  const uint32_t left = limit - off - pl.nstage * WSTAGE_BYTES;
+  static const bool noring = getenv("TTSB_UMMA_NORING") != nullptr;
+  // a slot holds rps rows per producer thread: 16-KB slots (two rows in flight per thread) when at least three fit, else 8 KB
+  pl.rps = 2;
+  pl.raw_bytes = (uint32_t)(2 * RPP) * pl.row_bytes;
+  if (!a.x_f16 && left / pl.raw_bytes < 3) { pl.rps = 1; pl.raw_bytes = (uint32_t)RPP * pl.row_bytes; }
+  pl.rch = pl.rps * RPP;
+  pl.nraw = (int)std::min<uint32_t>(left / pl.raw_bytes, a.x_f16 ? 6u : 4u);
+  if (pl.nraw < 2 || noring) pl.nraw = 0;
+  pl.nch = (pl.SR + pl.rch - 1) / pl.rch;
+  pl.off_raw = off; off += pl.nraw * pl.raw_bytes;
+  pl.off_w = off;
+  while (pl.nstage < MAXSTAGE && pl.off_w + (pl.nstage + 1) * WSTAGE_BYTES <= limit) ++pl.nstage;
+  pl.smem_bytes = pl.off_w + pl.nstage * WSTAGE_BYTES;
+  pl.items = a.ntiles;
+  return pl.smem_bytes <= limit;
+}
+
+int g_num_sms_wa[64] = {0};
+bool g_attr_set_wa[64] = {false};
+
+}  // namespace
+
+bool conv_umma_wa_supported(const ConvArgs& a) {
+  if (!a.wb || a.wfmt < 0 || a.wfmt > 1 || a.pro != PRO_ADAIN_SNAKE || a.stride != 1 || a.in_shr != 0 || a.act != ACT_NONE) return false;
+  if (a.tile_rows != TN || a.ldx != CH) return false;
+  if (a.acc_scale != 0.f && a.acc_scale != 1.0f) return false;
+  if (reinterpret_cast<uintptr_t>(a.x) & 15) return false;
+  if (a.y_f16 && (a.res || a.accumulate || a.out_scale != 1.0f)) return false;
+  if (!a.pstats || !a.gb || !a.alpha) return false;
+  WPlan pl;
+  return make_wplan(a, pl);
+}
+
+cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
+  if (a.ntiles <= 0) return cudaSuccess;
+  if (!conv_umma_wa_supported(a)) return cudaErrorInvalidValue;
+  WArgs u;
+  u.a = a;
+  if (!make_wplan(a, u.p)) return cudaErrorInvalidValue;
+  using KernelFn = void (*)(const WArgs);
+  // [wfmt][x_f16][y_f16]; an fp16 input with an fp16 output does not occur (c1 reads the fp32 residual stream, c2 writes it)
+  static const KernelFn table[2][2][2] = {
+      {{conv_umma_wa_kernel<0, false, false>, conv_umma_wa_kernel<0, false, true>}, {conv_umma_wa_kernel<0, true, false>, nullptr}},
+      {{conv_umma_wa_kernel<1, false, false>, conv_umma_wa_kernel<1, false, true>}, {conv_umma_wa_kernel<1, true, false>, nullptr}}};
+  const KernelFn kernel = table[a.wfmt][a.x_f16 ? 1 : 0][a.y_f16 ? 1 : 0];
+  if (!kernel) return cudaErrorInvalidValue;
+  int dev = 0;
+  {
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  }
+  if (!g_attr_set_wa[dev]) {
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j)
+        for (int k = 0; k < 2; ++k)
+          if (table[i][j][k]) {
+            cudaError_t e = cudaFuncSetAttribute(table[i][j][k], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return e;
+          }
+    cudaError_t e = cudaDeviceGetAttribute(&g_num_sms_wa[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    g_attr_set_wa[dev] = true;
+  }
+  static int prof_on = -1;
+  static long long* prof_buf = nullptr;
+  if (prof_on < 0) {
+    prof_on = getenv("TTSB_UMMA_PROF") ? 1 : 0;
+    if (prof_on && cudaMalloc(&prof_buf, sizeof(long long) * 16 * 256) != cudaSuccess) prof_on = 0;
+  }
+  u.prof = prof_on ? prof_buf : nullptr;
+  const int ncta = u.p.items < g_num_sms_wa[dev] ? u.p.items : g_num_sms_wa[dev];      // persistent: one CTA per SM
+  u.p.per_cta = (u.p.items + ncta - 1) / ncta;
+  const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
+  static cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  if (prof_on) {
+    if (!pe0) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
+    cudaEventRecord(pe0, s);
+  }
+  kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
+  if (prof_on) {      // diagnostic mode: synchronous, prints the mean cycle split of the roles for every launch
+    cudaEventRecord(pe1, s);
+    static long long host[16 * 256];
+    if (cudaStreamSynchronize(s) == cudaSuccess && cudaMemcpy(host, prof_buf, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      double m[9] = {0};
+      for (int cta = 0; cta < grid; ++cta)
+        for (int i = 0; i < 9; ++i) m[i] += (double)host[cta * 16 + i] / grid;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pe0, pe1);
+      fprintf(stderr, "umma_wa fmt=%d xh=%d yh=%d k=%d dil=%d grid=%d items/cta=%.1f SR=%d ring=%dx%uB wstages=%d | producer %.0f (wait %.0f) | mma %.0f (wait slab %.0f acc %.0f w %.0f) | epilogue %.0f (wait %.0f) cycles | %.1f us\n",
+              a.wfmt, a.x_f16, a.y_f16, a.k, a.dil, grid, m[8], u.p.SR, u.p.nraw, u.p.raw_bytes, u.p.nstage, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], ms * 1000.f);
+    }
+  }
+  return launched();
+}
+
+}  // namespace ttsb

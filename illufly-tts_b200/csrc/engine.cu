@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -13,6 +14,10 @@
 #include "../../include/ttsb200.h"
 
 namespace ttsb {
+
+// bounds that keep every row / sample count of a step inside int32 (600 samples and 120 stage-1 rows per frame)
+constexpr int MAX_DUR_PER_TOKEN = 1 << 16;
+constexpr long long MAX_FRAMES_PER_CALL = 1000000;     // 6.9 hours of audio; the workspace (~0.6 MB per frame) gives out long before
 
 long long g_launches = 0;
 static thread_local char g_err[1024] = "";
@@ -175,7 +180,7 @@ void Loader::pack_conv(const HostTensor& w, const std::vector<float>* bias, Conv
     c.wh = upload(pb);
   }
   if (want & 2) {
-    pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, 2, pb, c.cin_pad_s, c.cout_pad_s);
+    pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, 2, pb, c.cin_pad_s, c.cout_pad_s, &c.ws_scale);
     c.ws = upload(pb);
   }
 }
@@ -226,7 +231,7 @@ bool Loader::resblock1(const std::string& prefix, ResBlock1W& r, int C, int k, s
   bool ok = true;
   for (int m = 0; m < 3 && ok; ++m) {
     const std::string i = std::to_string(m);
-    ok = ok && conv(prefix + ".convs1." + i, r.c1[m], true, 1) && conv(prefix + ".convs2." + i, r.c2[m], true, 1);
+    ok = ok && conv(prefix + ".convs1." + i, r.c1[m], true, 3) && conv(prefix + ".convs2." + i, r.c2[m], true, 3);
     ok = ok && style_fc(prefix + ".adain1." + i + ".fc", 2 * C, sw, sb, r.a1[m], C) && style_fc(prefix + ".adain2." + i + ".fc", 2 * C, sw, sb, r.a2[m], C);
     r.alpha1[m] = upload_named(prefix + ".alpha1." + i);
     r.alpha2[m] = upload_named(prefix + ".alpha2." + i);
@@ -256,7 +261,7 @@ bool pack_convT(Loader& ld, const std::string& prefix, int stride, ConvW& c) {
         dst[1] = w.data[((size_t)ci * Cout + co) * K + r];            // tap 1 reads x[m]
       }
     }
-  ld.pack_conv(p, &bias, c, 1);
+  ld.pack_conv(p, &bias, c, 3);
   return true;
 }
 
@@ -299,8 +304,8 @@ int engine_finalize(Engine& e) {
   ok = ok && ld.conv("predictor.duration_proj.linear_layer", e.dur_proj, true, 2);
   const int pc[3][2] = {{512, 512}, {512, 256}, {256, 256}};
   for (int i = 0; i < 3 && ok; ++i) {
-    ok = ok && ld.resblk1d("predictor.F0." + std::to_string(i), e.f0_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, 1);
-    ok = ok && ld.resblk1d("predictor.N." + std::to_string(i), e.n_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, 1);
+    ok = ok && ld.resblk1d("predictor.F0." + std::to_string(i), e.f0_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, 3);
+    ok = ok && ld.resblk1d("predictor.N." + std::to_string(i), e.n_blk[i], pc[i][0], pc[i][1], i == 1, swP, sbP, 3);
   }
   ok = ok && ld.conv("predictor.F0_proj", e.f0_proj) && ld.conv("predictor.N_proj", e.n_proj);
   e.te_emb = ld.upload_named("text_encoder.embedding.weight");
@@ -310,10 +315,10 @@ int engine_finalize(Engine& e) {
     e.te_ln_g[l] = ld.upload_named(p + ".1.gamma");
     e.te_ln_b[l] = ld.upload_named(p + ".1.beta");
   }
-  ok = ok && ld.resblk1d("decoder.encode", e.enc_blk, 514, 1024, false, swD, sbD, 1);
+  ok = ok && ld.resblk1d("decoder.encode", e.enc_blk, 514, 1024, false, swD, sbD, 3);
   for (int i = 0; i < 4 && ok; ++i)
-    ok = ok && ld.resblk1d("decoder.decode." + std::to_string(i), e.dec_blk[i], 1090, i == 3 ? 512 : 1024, i == 3, swD, sbD, 1);
-  ok = ok && ld.conv("decoder.asr_res.0", e.asr_res, true, 1);
+    ok = ok && ld.resblk1d("decoder.decode." + std::to_string(i), e.dec_blk[i], 1090, i == 3 ? 512 : 1024, i == 3, swD, sbD, 3);
+  ok = ok && ld.conv("decoder.asr_res.0", e.asr_res, true, 3);
   {
     HostTensor w;
     if (ld.weight("decoder.F0_conv", w)) e.f0conv_w = ld.upload(w.data); else ok = false;
@@ -324,7 +329,7 @@ int engine_finalize(Engine& e) {
   const std::string G = "decoder.generator.";
   e.src_lin_w = ld.upload_named(G + "m_source.l_linear.weight");
   e.src_lin_b = ld.upload_named(G + "m_source.l_linear.bias");
-  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, 0) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, 1);
+  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, 0) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, 3);
   if (ok) {
     // noise_convs[0]: Conv1d(22, 256, k12, stride 6, pad 3) over STFT frames == k3/pad1 conv over frames regrouped six at a time
     // ([blocks, 6 x 24] view of the channels-last har buffer): tap in {0,1,2}, slot i in 0..5  <->  original tap j = 6 tap + i - 3
@@ -340,14 +345,14 @@ int engine_finalize(Engine& e) {
             if (j < 0 || j >= 12) continue;
             for (int c = 0; c < 22; ++c) wr.data[((size_t)co * 144 + i * 24 + c) * 3 + tap] = w0->data[((size_t)co * 22 + c) * 12 + j];
           }
-      ld.pack_conv(wr, &b0->data, e.noise_conv0r, 1);
+      ld.pack_conv(wr, &b0->data, e.noise_conv0r, 3);
     } else ok = false;
   }
   ok = ok && pack_convT(ld, G + "ups.0", 10, e.ups[0]) && pack_convT(ld, G + "ups.1", 6, e.ups[1]);
   ok = ok && ld.resblock1(G + "noise_res.0", e.noise_res[0], 256, 7, swD, sbD) && ld.resblock1(G + "noise_res.1", e.noise_res[1], 128, 11, swD, sbD);
   const int rk[3] = {3, 7, 11};
   for (int i = 0; i < 6 && ok; ++i) ok = ok && ld.resblock1(G + "resblocks." + std::to_string(i), e.resblk[i], i < 3 ? 256 : 128, rk[i % 3], swD, sbD);
-  ok = ok && ld.conv(G + "conv_post", e.conv_post, true, 1);
+  ok = ok && ld.conv(G + "conv_post", e.conv_post, true, 3);
   if (ok) {
     HostTensor w;
     w.shape = {(int64_t)sbP.size(), 128}; w.data = swP; ld.pack_conv(w, &sbP, e.style_pred, 0);
@@ -502,13 +507,22 @@ struct ConvCall {
   bool exact = false;            // text side: tcgen05 with split-fp16 operands (fp32-equivalent) in tensor precisions, FFMA in FP32
 };
 
+// Which kernel a convolution runs on, by precision mode:
+//   FP32 (the strict tier)  every tensor-eligible layer, text side and frame side, on tcgen05 with split-fp16 operands (fp32-class
+//                           products, 3 MMAs per K step); the FFMA kernel only where the tcgen05 kernel does not support the shape
+//   FP32_FFMA               the CUDA-core fp32 kernel everywhere (the arithmetic reference of the strict tier; tests)
+//   BF16 / FP16             text side (c.exact) split-fp16, frame side (c.tensor) 16-bit operands
 int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
-  const bool f16 = r.e.precision == TTSB_PRECISION_FP16;
+  const int prec = r.e.precision;
+  const bool f16 = prec == TTSB_PRECISION_FP16;
+  const bool ffma_only = prec == TTSB_PRECISION_FP32_FFMA;
+  const bool split = !ffma_only && c.w->ws != nullptr && (c.exact || (c.tensor && prec == TTSB_PRECISION_FP32));
+  const bool half16 = !ffma_only && !split && c.tensor && !c.exact && (prec == TTSB_PRECISION_FP16 || prec == TTSB_PRECISION_BF16);
   a.x = c.x; a.ldx = c.ldx; a.w = c.w->w; a.ldw = c.w->ldw;
-  if (c.exact) { a.wb = c.w->ws; a.wfmt = 2; a.cin_pad = c.w->cin_pad_s; a.cout_pad = c.w->cout_pad_s; }
-  else { a.wb = f16 ? c.w->wh : c.w->wb; a.wfmt = f16 ? 1 : 0; a.cin_pad = c.w->cin_pad; a.cout_pad = c.w->cout_pad; }
+  if (split) { a.wb = c.w->ws; a.wfmt = 2; a.cin_pad = c.w->cin_pad_s; a.cout_pad = c.w->cout_pad_s; a.split_wscale = c.w->ws_scale; a.sat = r.e.d_sat; }
+  else if (half16) { a.wb = f16 ? c.w->wh : c.w->wb; a.wfmt = f16 ? 1 : 0; a.cin_pad = c.w->cin_pad; a.cout_pad = c.w->cout_pad; }
   a.bias = c.w->bias; a.y = c.y; a.ldy = c.ldy; a.res = c.res; a.ldr = c.ldr;
   a.Cin = c.w->Cin; a.Cout = c.w->Cout; a.k = c.w->k; a.dil = c.dil; a.pad = c.pad; a.stride = c.stride; a.in_shr = c.in_shr;
   a.pro = c.pro; a.slope = c.slope;
@@ -518,9 +532,8 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   a.out_scale = c.out_scale; a.accumulate = c.accumulate; a.act = c.act; a.act_slope = c.act_slope;
   a.ostats = c.ostats; a.ld_ostats = c.w->Cout;
   a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
-  if ((c.exact || c.tensor) && r.e.precision != TTSB_PRECISION_FP32 && a.stride == 1) {
+  if ((split || half16) && a.stride == 1) {
     // layers with several Cout tiles read pre-packed operand images (conv_umma.cu: pack_act_kernel); scratch sized for this call
-    const bool split = c.exact;
     const int ks = split ? 64 : (a.cin_pad < 128 ? a.cin_pad : 128);
     const int bn = split ? 128 : 256;
     if (a.cout_pad > bn) {
@@ -540,10 +553,15 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   const double rows = (double)t.out_rows;
   const double fl = 2.0 * rows * a.Cin * a.Cout * a.k;
   const double by = 4.0 * rows * ((double)a.Cout * (1 + (a.res ? 1 : 0) + (a.accumulate ? 1 : 0))) + 4.0 * (double)t.in_rows * a.Cin;
-  if ((c.tensor || c.exact) && r.e.precision != TTSB_PRECISION_FP32 && conv_umma_supported(a)) {
+  if ((split || half16) && conv_umma_supported(a)) {
     r.e.prof.begin(r.s, PROF_CONV_TENSOR, fl, by);
     CK(launch_conv_umma(a, r.s));
   } else {
+    static const bool conv_log = getenv("TTSB_CONV_LOG") != nullptr;
+    if (conv_log && (split || half16))
+      fprintf(stderr, "ttsb: conv Cin=%d Cout=%d k=%d dil=%d ldx=%d ldy=%d in_shr=%d wfmt=%d falls back to the FFMA kernel\n", a.Cin, a.Cout, a.k, a.dil, a.ldx, a.ldy,
+              a.in_shr, a.wfmt);
+    a.wb = nullptr; a.wfmt = 0; a.sat = nullptr;
     r.e.prof.begin(r.s, PROF_CONV_SIMT, fl, by);
     CK(launch_conv_simt(a, r.s));
   }
@@ -744,7 +762,8 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   RC(run_conv(r, cpc, tS1));
   RC(r.tap("conv_post", cp, spS1.total, 22, 24));
   e.prof.begin(r.s, PROF_ISTFT, 0.0, 4.0 * (22.0 * spS1.total + (double)spA.total));
-  CK(launch_istft(cp, 24, audio, tS1_A.segs, nseg, spS1.maxlen, r.s));
+  const bool precise = e.precision == TTSB_PRECISION_FP32 || e.precision == TTSB_PRECISION_FP32_FFMA;
+  CK(launch_istft(cp, 24, audio, tS1_A.segs, nseg, spS1.maxlen, precise, r.s));
   e.prof.end(r.s);
   return TTSB_OK;
 }
@@ -755,7 +774,7 @@ int run_style(Run& r, const ConvW& w, const float* style, int ld_style, int nseg
   if (!gb) return TTSB_E_NOMEM;
   static const bool use_simt = getenv("TTSB_STYLE_SIMT") != nullptr;     // the tiled fp32 conv kernel: kept for bit-for-bit checks
   if (!use_simt && w.k == 1 && w.Cin <= 128) {
-    r.e.prof.begin(r.s, PROF_CONV_SIMT, 2.0 * nseg * w.Cin * w.Cout, 4.0 * ((double)w.Cin * w.Cout + (double)nseg * w.Cout));
+    r.e.prof.begin(r.s, PROF_PROJ, 2.0 * nseg * w.Cin * w.Cout, 4.0 * ((double)w.Cin * w.Cout + (double)nseg * w.Cout));
     CK(launch_style_proj(style, ld_style, nseg, w.w, w.ldw, w.bias, gb, w.ldw, w.Cin, w.Cout, r.s));
     r.e.prof.end(r.s);
     *out = gb;
@@ -786,6 +805,7 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   Run r(e);
   e.prof.reset();
   CK(cudaEventRecord(e.ev_step0, r.s));
+  CK(cudaMemsetAsync(e.d_sat, 0, sizeof(unsigned int), r.s));
   std::vector<int> lens(B);
   int Tmax = 0;
   for (int b = 0; b < B; ++b) {
@@ -799,6 +819,15 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   const int R = e.spT.total;
   for (int i = 0; i < R; ++i)
     if (ids[token_offsets[0] + i] < 0 || ids[token_offsets[0] + i] >= 178) { set_error("begin: token id out of range at %d", i); return TTSB_E_INVALID; }
+  // a speed of 0, a negative, a denormal-small or a non-finite one would turn sum(sigmoid) / speed (kmodel.py:102) into inf or ~1e10
+  // frames per token (the reference then fails inside torch and answers with silence, kmodel.py:147-150); refuse it here.
+  // 50 bins / speed frames per token at most: speed >= 1e-3 bounds a token at 50 000 frames.
+  if (speeds)
+    for (int b = 0; b < B; ++b)
+      if (!(speeds[b] >= 1e-3f) || !(speeds[b] <= 1e3f)) { set_error("begin: speed of utterance %d is %g (must be finite, in [1e-3, 1e3])", b, (double)speeds[b]); return TTSB_E_INVALID; }
+  if (forced_dur)
+    for (int i = 0; i < R; ++i)
+      if (forced_dur[i] < 1 || forced_dur[i] > MAX_DUR_PER_TOKEN) { set_error("begin: forced_dur[%d] = %d (must be in [1, %d])", i, forced_dur[i], MAX_DUR_PER_TOKEN); return TTSB_E_INVALID; }
 
   // ---- tables + inputs, one upload ----
   RC(r.tables_begin((size_t)B * (sizeof(Seg) + 2 * sizeof(LstmGroup) + 260 * sizeof(float)) + (size_t)(R / 128 + B + 8) * sizeof(Tile) + (size_t)R * 16 + 8192));
@@ -900,11 +929,24 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   CK(launch_duration(logits, 52, 50, d_r2s, d_speed, d_dur, d_pd, R, r.s));
   const int* d_used = d_forced ? d_forced : d_pd;
   CK(launch_dur_scan(d_used, tT.segs, B, d_cum, d_tot, r.s));
-  // results the host needs to size the frame side
-  std::vector<int> h_tot(B);
-  CK(cudaMemcpyAsync(pred_dur, d_pd, sizeof(int) * R, cudaMemcpyDeviceToHost, r.s));
-  if (duration) CK(cudaMemcpyAsync(duration, d_dur, sizeof(float) * R, cudaMemcpyDeviceToHost, r.s));
-  CK(cudaMemcpyAsync(h_tot.data(), d_tot, sizeof(int) * B, cudaMemcpyDeviceToHost, r.s));
+  // results the host needs to size the frame side: through PINNED memory, so that the copies are asynchronous and the text
+  // encoder queued below really overlaps the host's wait (a D2H copy into pageable memory blocks the calling thread)
+  const size_t out_bytes = sizeof(int) * (size_t)R + sizeof(float) * (size_t)R + sizeof(int) * (size_t)B + sizeof(unsigned int) + 64;
+  if (out_bytes > e.pinned_out_cap) {
+    if (e.pinned_out) cudaFreeHost(e.pinned_out);
+    e.pinned_out = nullptr; e.pinned_out_cap = 0;
+    const size_t cap = std::max(out_bytes * 2, size_t(1) << 16);
+    CK(cudaMallocHost(&e.pinned_out, cap));
+    e.pinned_out_cap = cap;
+  }
+  int* h_pd = reinterpret_cast<int*>(e.pinned_out);
+  float* h_dur = reinterpret_cast<float*>(h_pd + R);
+  int* h_tot = reinterpret_cast<int*>(h_dur + R);
+  unsigned int* h_sat = reinterpret_cast<unsigned int*>(h_tot + B);
+  CK(cudaMemcpyAsync(h_pd, d_pd, sizeof(int) * R, cudaMemcpyDeviceToHost, r.s));
+  CK(cudaMemcpyAsync(h_dur, d_dur, sizeof(float) * R, cudaMemcpyDeviceToHost, r.s));
+  CK(cudaMemcpyAsync(h_tot, d_tot, sizeof(int) * B, cudaMemcpyDeviceToHost, r.s));
+  CK(cudaMemcpyAsync(h_sat, e.d_sat, sizeof(unsigned int), cudaMemcpyDeviceToHost, r.s));
   CK(cudaEventRecord(e.ev0, r.s));
   e.d_pred_dur = d_pd; e.d_cum = d_cum;
 
@@ -931,11 +973,51 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   }
 
   CK(cudaEventSynchronize(e.ev0));
+  memcpy(pred_dur, h_pd, sizeof(int) * R);
+  if (duration) memcpy(duration, h_dur, sizeof(float) * R);
+  if (*h_sat != 0) {
+    set_error("begin: %u operand conversions of the split-fp16 (fp32-class) tensor-core path left fp16's range (|x| > 4094) on the text side: "
+              "the durations would be wrong.  Run this checkpoint with TTSB_PRECISION_FP32_FFMA", *h_sat);
+    return TTSB_E_RANGE;
+  }
   std::vector<int> fl(B);
   frame_offsets[0] = 0;
-  for (int b = 0; b < B; ++b) { fl[b] = h_tot[b]; frame_offsets[b + 1] = frame_offsets[b] + h_tot[b]; }
+  long long total = 0;
+  for (int b = 0; b < B; ++b) {
+    if (h_tot[b] <= 0) { set_error("begin: utterance %d has a frame count of %d (duration overflow)", b, h_tot[b]); return TTSB_E_TOO_LONG; }
+    total += h_tot[b];
+    if (total > MAX_FRAMES_PER_CALL) { set_error("begin: the batch needs more than %lld frames (%.1f hours of audio)", MAX_FRAMES_PER_CALL, MAX_FRAMES_PER_CALL / 40.0 / 3600.0); return TTSB_E_TOO_LONG; }
+    fl[b] = h_tot[b]; frame_offsets[b + 1] = frame_offsets[b] + h_tot[b];
+  }
   e.spF.build(fl);
   e.begun = true;
+  return TTSB_OK;
+}
+
+// End of a step.  The strict tier (split-fp16 operands on the frame side too) always waits for the stream and reads the operand
+// range counter: a saturated conversion would silently break the "fp32-class" promise, so it is an error, not a statistic.
+static int finish_step(Engine& e, cudaStream_t s, bool must_sync) {
+  const bool strict = e.precision == TTSB_PRECISION_FP32;
+  unsigned int* h_sat = nullptr;
+  if (strict) {
+    if (e.pinned_out_cap < 64) {
+      if (e.pinned_out) cudaFreeHost(e.pinned_out);
+      e.pinned_out = nullptr; e.pinned_out_cap = 0;
+      CK(cudaMallocHost(&e.pinned_out, size_t(1) << 16));
+      e.pinned_out_cap = size_t(1) << 16;
+    }
+    h_sat = reinterpret_cast<unsigned int*>(e.pinned_out);
+    CK(cudaMemcpyAsync(h_sat, e.d_sat, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+  }
+  if (must_sync || strict || e.taps_on || e.prof.on) {
+    CK(cudaStreamSynchronize(s));
+    e.prof.collect();
+  }
+  if (strict && *h_sat != 0) {
+    set_error("%u operand conversions of the split-fp16 (fp32-class) tensor-core path left fp16's range (|x| > 4094): the waveform is "
+              "not fp32-class.  Run this checkpoint with TTSB_PRECISION_FP32_FFMA", *h_sat);
+    return TTSB_E_RANGE;
+  }
   return TTSB_OK;
 }
 
@@ -963,7 +1045,8 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   const SegTab tL = r.make_tab(spL, spL);
   const SegTab tFL = r.make_tab(spF, spL);
   const SegTab tLF = r.make_tab(spL, spF, 1, 1, false);
-  std::vector<int> f2s(RF);
+  if (RF <= 0 || (long long)RF > MAX_FRAMES_PER_CALL) { set_error("finish: bad frame count %d", RF); return TTSB_E_INVALID; }
+  std::vector<int> f2s((size_t)RF);
   std::vector<LstmSeg> lsF(B);
   for (int b = 0; b < B; ++b) {
     for (int f = 0; f < spF.len[b]; ++f) f2s[spF.off[b] + f] = b;
@@ -1034,7 +1117,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
     const ConvW& pw = br == 0 ? e.f0_proj : e.n_proj;
     static const bool proj_simt = getenv("TTSB_ROWDOT_SIMT") != nullptr;        // the tiled fp32 conv kernel: kept for bit-for-bit checks
     if (!proj_simt && pw.k == 1 && pw.Cout == 1 && pw.Cin <= 512) {
-      r.e.prof.begin(r.s, PROF_CONV_SIMT, 2.0 * RL * pw.Cin, 4.0 * RL * (pw.Cin + 1.0));
+      r.e.prof.begin(r.s, PROF_PROJ, 2.0 * RL * pw.Cin, 4.0 * RL * (pw.Cin + 1.0));
       CK(launch_rowdot(o2, 256, RL, pw.Cin, pw.w, pw.ldw, pw.bias, br == 0 ? F0 : NN, 1, r.s));
       r.e.prof.end(r.s);
     } else {
@@ -1104,10 +1187,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   RC(run_generator(r, spL, GIN, F0, gbD, ldD, d_noise, seed, (int)utt_seeds.size() == spL.n() ? &utt_seeds : nullptr, d_audio));
   if (audio_mem != TTSB_MEM_DEVICE) CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * (size_t)RF * 600, cudaMemcpyDeviceToHost, r.s));
   CK(cudaEventRecord(e.ev_step1, r.s));
-  if (audio_mem != TTSB_MEM_DEVICE || indices || e.taps_on || e.prof.on) {
-    CK(cudaStreamSynchronize(r.s));
-    e.prof.collect();
-  }
+  RC(finish_step(e, r.s, audio_mem != TTSB_MEM_DEVICE || indices != nullptr));
   return TTSB_OK;
 }
 
@@ -1124,6 +1204,7 @@ int engine_vocoder(Engine& e, const float* x, const float* f0, const float* styl
   Run r(e);
   e.prof.reset();
   CK(cudaEventRecord(e.ev_step0, r.s));
+  CK(cudaMemsetAsync(e.d_sat, 0, sizeof(unsigned int), r.s));
   std::vector<int> lL(B);
   for (int b = 0; b < B; ++b) {
     lL[b] = l_offsets[b + 1] - l_offsets[b];
@@ -1157,10 +1238,7 @@ int engine_vocoder(Engine& e, const float* x, const float* f0, const float* styl
   RC(run_generator(r, spL, dx, df0, gbD, e.style_dec.ldw, dnoise, seed, nullptr, d_audio));   // no token ids here: noise keyed by buffer position
   if (audio_mem != TTSB_MEM_DEVICE) CK(cudaMemcpyAsync(audio, d_audio, sizeof(float) * RL * 300, cudaMemcpyDeviceToHost, r.s));
   CK(cudaEventRecord(e.ev_step1, r.s));
-  if (audio_mem != TTSB_MEM_DEVICE || e.taps_on || e.prof.on) {
-    CK(cudaStreamSynchronize(r.s));
-    e.prof.collect();
-  }
+  RC(finish_step(e, r.s, audio_mem != TTSB_MEM_DEVICE));
   return TTSB_OK;
 }
 

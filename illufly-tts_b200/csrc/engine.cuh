@@ -24,6 +24,7 @@ struct ConvW {
   uint16_t* ws = nullptr;                 // split-fp16 UMMA pack (hi | lo), or null: fp32-equivalent tensor-core path
   int cin_pad = 0, cout_pad = 0;
   int cin_pad_s = 0, cout_pad_s = 0;
+  float ws_scale = 0.f;                   // power of two the split pack's weights were scaled by (chosen from max|w| of the layer)
   int Cin = 0, Cout = 0, k = 1;
 };
 struct LstmW {
@@ -65,7 +66,7 @@ struct Tap { float* d = nullptr; int64_t rows = 0, cols = 0; };
 
 // per-category device time of the last step, from CUDA events recorded around the launches on the engine's stream
 enum ProfCat : int { PROF_CONV_TENSOR = 0, PROF_CONV_SIMT = 1, PROF_LSTM = 2, PROF_ISTFT = 3, PROF_ELEMENTWISE = 4, PROF_GATHER = 5, PROF_ATTENTION = 6, PROF_LAYERNORM = 7,
-                     PROF_SOURCE = 8, PROF_NCAT = 9 };
+                     PROF_SOURCE = 8, PROF_PROJ = 9 /* style projections, F0_proj / N_proj: fp32 row kernels */, PROF_NCAT = 10 };
 struct ProfRec { int cat; double flops, bytes; };
 struct Profiler {
   bool on = false;
@@ -124,6 +125,8 @@ struct Engine {
   std::map<std::string, Tap> taps;
   Arena arena;
   char* pinned = nullptr; size_t pinned_cap = 0;
+  char* pinned_out = nullptr; size_t pinned_out_cap = 0;   // begin(): durations / totals / range counter come back through pinned memory
+  unsigned int* d_sat = nullptr;          // split-fp16 operand range counter (ConvArgs::sat), zeroed at the start of a step
 
   // ---- weights ----
   float *emb_word = nullptr, *emb_pos = nullptr, *emb_type = nullptr, *emb_ln_g = nullptr, *emb_ln_b = nullptr;

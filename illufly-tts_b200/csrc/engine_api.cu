@@ -1,10 +1,11 @@
-// C ABI (include/ttsb200.h) over the engine.  Every function catches nothing because nothing below throws on the
-// hot path; allocation failures of std containers at load time are mapped to TTSB_E_NOMEM.
+// C ABI (include/ttsb200.h) over the engine.  No C++ exception crosses `extern "C"`: every entry point that reaches std containers
+// runs inside GUARD (std::bad_alloc -> TTSB_E_NOMEM, any other std::exception -> TTSB_E_INVALID with its message).
 #include "engine.cuh"
 
 #include <math.h>
 #include <string.h>
 
+#include <exception>
 #include <new>
 
 #include "../../include/ttsb200.h"
@@ -23,6 +24,16 @@ struct ttsb_engine {
       return TTSB_E_CUDA;                                                                               \
     }                                                                                                   \
   } while (0)
+
+#define GUARD(where, body)                                                                               \
+  try { body } catch (const std::bad_alloc&) { set_error(where ": out of host memory"); return TTSB_E_NOMEM; } \
+  catch (const std::exception& ex) { set_error(where ": %s", ex.what()); return TTSB_E_INVALID; }              \
+  catch (...) { set_error(where ": unknown C++ exception"); return TTSB_E_INVALID; }
+
+#define GUARD_END(where)                                                                                 \
+  catch (const std::bad_alloc&) { set_error(where ": out of host memory"); return TTSB_E_NOMEM; }        \
+  catch (const std::exception& ex) { set_error(where ": %s", ex.what()); return TTSB_E_INVALID; }        \
+  catch (...) { set_error(where ": unknown C++ exception"); return TTSB_E_INVALID; }
 
 namespace {
 
@@ -89,16 +100,24 @@ int ttsb_engine_create(int cuda_device, ttsb_engine** out) {
   CKA(cudaSetDevice(cuda_device));
   cudaDeviceProp prop;
   CKA(cudaGetDeviceProperties(&prop, cuda_device));
-  if (prop.major != 10) { set_error("create: device %d is sm_%d%d; this library is built for sm_100a only", cuda_device, prop.major, prop.minor); return TTSB_E_CUDA; }
-  ttsb_engine* h = new (std::nothrow) ttsb_engine();
-  if (!h) { set_error("create: out of host memory"); return TTSB_E_NOMEM; }
+  // the library carries one sm_100a cubin and no PTX: sm_103 (B300) would fail later with "no kernel image"
+  if (prop.major != 10 || prop.minor != 0) { set_error("create: device %d is sm_%d%d; this library is built for sm_100a only", cuda_device, prop.major, prop.minor); return TTSB_E_CUDA; }
+  ttsb_engine* h = nullptr;
+  GUARD("create", h = new ttsb_engine();)
   h->e.device = cuda_device;
-  CKA(cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking));
-  CKA(cudaEventCreate(&h->e.ev0));
-  CKA(cudaEventCreate(&h->e.ev1));
-  CKA(cudaEventCreateWithFlags(&h->e.ev_sync, cudaEventDisableTiming));
-  CKA(cudaEventCreate(&h->e.ev_step0));
-  CKA(cudaEventCreate(&h->e.ev_step1));
+  auto setup = [&]() -> int {
+    CKA(cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking));
+    CKA(cudaEventCreate(&h->e.ev0));
+    CKA(cudaEventCreate(&h->e.ev1));
+    CKA(cudaEventCreateWithFlags(&h->e.ev_sync, cudaEventDisableTiming));
+    CKA(cudaEventCreate(&h->e.ev_step0));
+    CKA(cudaEventCreate(&h->e.ev_step1));
+    CKA(cudaMalloc(&h->e.d_sat, 256));
+    CKA(cudaMemset(h->e.d_sat, 0, 256));
+    return TTSB_OK;
+  };
+  const int rc = setup();
+  if (rc != TTSB_OK) { ttsb_engine_destroy(h); return rc; }      // whatever was created so far is released (the message stays)
   *out = h;
   return TTSB_OK;
 }
@@ -112,6 +131,8 @@ int ttsb_engine_destroy(ttsb_engine* h) {
   for (auto& kv : e.taps) if (kv.second.d) cudaFree(kv.second.d);
   e.arena.release();
   if (e.pinned) cudaFreeHost(e.pinned);
+  if (e.pinned_out) cudaFreeHost(e.pinned_out);
+  if (e.d_sat) cudaFree(e.d_sat);
   if (e.ev0) cudaEventDestroy(e.ev0);
   if (e.ev1) cudaEventDestroy(e.ev1);
   if (e.ev_sync) cudaEventDestroy(e.ev_sync);
@@ -130,21 +151,20 @@ int ttsb_engine_set_tensor(ttsb_engine* h, const char* name, const float* data, 
   t.shape.assign(shape, shape + ndim);
   const int64_t n = t.numel();
   if (n <= 0) { set_error("set_tensor: '%s' is empty", name); return TTSB_E_INVALID; }
-  try {
+  GUARD("set_tensor",
     t.data.assign(data, data + n);
-    h->e.host[name] = std::move(t);
-  } catch (const std::bad_alloc&) { set_error("set_tensor: out of host memory"); return TTSB_E_NOMEM; }
+    h->e.host[name] = std::move(t);)
   return TTSB_OK;
 }
 
 int ttsb_engine_finalize(ttsb_engine* h) {
   if (!h) { set_error("finalize: engine is NULL"); return TTSB_E_INVALID; }
   CKA(cudaSetDevice(h->e.device));
-  try { return engine_finalize(h->e); } catch (const std::bad_alloc&) { set_error("finalize: out of host memory"); return TTSB_E_NOMEM; }
+  GUARD("finalize", return engine_finalize(h->e);)
 }
 
 int ttsb_engine_set_precision(ttsb_engine* h, int precision) {
-  if (!h || (precision != TTSB_PRECISION_FP32 && precision != TTSB_PRECISION_BF16 && precision != TTSB_PRECISION_FP16)) { set_error("set_precision: bad arguments"); return TTSB_E_INVALID; }
+  if (!h || precision < TTSB_PRECISION_FP32 || precision > TTSB_PRECISION_FP32_FFMA) { set_error("set_precision: bad arguments"); return TTSB_E_INVALID; }
   h->e.precision = precision;
   return TTSB_OK;
 }
@@ -181,24 +201,18 @@ int ttsb_engine_profile_read(ttsb_engine* h, int category, double* ms, double* f
 int ttsb_synthesize_begin(ttsb_engine* h, const int32_t* ids, const int32_t* token_offsets, int B, const float* ref_s, const float* speeds,
                           int padded_lstm, const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets) {
   if (!h) { set_error("begin: engine is NULL"); return TTSB_E_INVALID; }
-  try {
-    return engine_begin(h->e, ids, token_offsets, B, ref_s, speeds, padded_lstm, forced_dur, pred_dur, duration, frame_offsets);
-  } catch (const std::bad_alloc&) { set_error("begin: out of host memory"); return TTSB_E_NOMEM; }
+  GUARD("begin", return engine_begin(h->e, ids, token_offsets, B, ref_s, speeds, padded_lstm, forced_dur, pred_dur, duration, frame_offsets);)
 }
 
 int ttsb_synthesize_finish(ttsb_engine* h, const float* noise, int noise_mem, uint64_t seed, int32_t* indices, float* audio, int audio_mem) {
   if (!h) { set_error("finish: engine is NULL"); return TTSB_E_INVALID; }
-  try {
-    return engine_finish(h->e, noise, noise_mem, seed, indices, audio, audio_mem);
-  } catch (const std::bad_alloc&) { set_error("finish: out of host memory"); return TTSB_E_NOMEM; }
+  GUARD("finish", return engine_finish(h->e, noise, noise_mem, seed, indices, audio, audio_mem);)
 }
 
 int ttsb_vocoder(ttsb_engine* h, const float* x, const float* f0, const float* style, const int32_t* l_offsets, int B, int in_mem, const float* noise,
                  uint64_t seed, float* audio, int audio_mem) {
   if (!h) { set_error("vocoder: engine is NULL"); return TTSB_E_INVALID; }
-  try {
-    return engine_vocoder(h->e, x, f0, style, l_offsets, B, in_mem, noise, seed, audio, audio_mem);
-  } catch (const std::bad_alloc&) { set_error("vocoder: out of host memory"); return TTSB_E_NOMEM; }
+  GUARD("vocoder", return engine_vocoder(h->e, x, f0, style, l_offsets, B, in_mem, noise, seed, audio, audio_mem);)
 }
 
 int ttsb_engine_read_tap(ttsb_engine* h, const char* name, float* out, int64_t* rows, int64_t* cols) {
@@ -218,7 +232,7 @@ int ttsb_engine_read_tap(ttsb_engine* h, const char* name, float* out, int64_t* 
 // ---------------------------------------------------------------------------------------------------------
 // single-kernel entry points
 // ---------------------------------------------------------------------------------------------------------
-int ttsb_op_istft(ttsb_engine* h, const float* cp, int ld, const int32_t* frame_counts_F, int B, float* audio, float* ms) {
+int ttsb_op_istft(ttsb_engine* h, const float* cp, int ld, const int32_t* frame_counts_F, int B, float* audio, float* ms) try {
   if (!h || !cp || !frame_counts_F || B <= 0 || !audio || ld < 24 || (ld & 3)) { set_error("op_istft: bad arguments (rows must hold >= 24 floats, 16-byte aligned)"); return TTSB_E_INVALID; }
   Engine& e = h->e;
   CKA(cudaSetDevice(e.device));
@@ -232,13 +246,13 @@ int ttsb_op_istft(ttsb_engine* h, const float* cp, int ld, const int32_t* frame_
   for (int b = 0; b < B; ++b) maxf = std::max(maxf, fi[b]);
   OpTimer tm(e, ms);
   CKA(tm.start());
-  CKA(launch_istft(cp, ld, audio, t.segs, B, maxf, e.stream));
+  CKA(launch_istft(cp, ld, audio, t.segs, B, maxf, e.precision == TTSB_PRECISION_FP32 || e.precision == TTSB_PRECISION_FP32_FFMA, e.stream));
   CKA(tm.stop());
   return TTSB_OK;
-}
+} GUARD_END("op_istft")
 
 int ttsb_op_adain_snake(ttsb_engine* h, const float* x, float* y, int C, const int32_t* row_offsets, int B, const float* gamma_beta, const float* alpha,
-                        float* ms_stats, float* ms_apply) {
+                        float* ms_stats, float* ms_apply) try {
   if (!h || !x || !y || !row_offsets || B <= 0 || !gamma_beta || !alpha || C <= 0 || (C & 3)) { set_error("op_adain_snake: bad arguments"); return TTSB_E_INVALID; }
   Engine& e = h->e;
   CKA(cudaSetDevice(e.device));
@@ -264,10 +278,10 @@ int ttsb_op_adain_snake(ttsb_engine* h, const float* x, float* y, int C, const i
   }
   CKA(cudaStreamSynchronize(e.stream));
   return TTSB_OK;
-}
+} GUARD_END("op_adain_snake")
 
 int ttsb_op_length_regulate(ttsb_engine* h, const int32_t* pred_dur, const int32_t* token_offsets, int B, const float* src, int C, int32_t* indices,
-                            float* dst, int32_t* frame_offsets_host, float* ms) {
+                            float* dst, int32_t* frame_offsets_host, float* ms) try {
   if (!h || !pred_dur || !token_offsets || B <= 0 || !src || !indices || !dst || !frame_offsets_host || C <= 0 || (C & 3)) {
     set_error("op_length_regulate: bad arguments"); return TTSB_E_INVALID;
   }
@@ -307,10 +321,10 @@ int ttsb_op_length_regulate(ttsb_engine* h, const int32_t* pred_dur, const int32
   CKA(tm.stop());
   CKA(cudaStreamSynchronize(e.stream));
   return TTSB_OK;
-}
+} GUARD_END("op_length_regulate")
 
 int ttsb_op_conv1d(ttsb_engine* h, const float* x, const float* w, const float* bias, float* y, int Cin, int Cout, int k, int dilation,
-                   const int32_t* row_offsets, int B, int precision, int reps, float* ms) {
+                   const int32_t* row_offsets, int B, int precision, int reps, float* ms) try {
   if (!h || !x || !w || !y || !row_offsets || B <= 0 || Cin <= 0 || Cout <= 0 || k <= 0 || dilation <= 0 || (Cin & 3)) {
     set_error("op_conv1d: bad arguments"); return TTSB_E_INVALID;
   }
@@ -329,8 +343,10 @@ int ttsb_op_conv1d(ttsb_engine* h, const float* x, const float* w, const float* 
       for (int j = 0; j < k; ++j) p[((size_t)j * Cin + ci) * ldw + co] = w[((size_t)co * Cin + ci) * k + j];
   std::vector<uint16_t> pb;
   int cin_pad = 0, cout_pad = 0;
-  const int wfmt = precision == 3 ? 2 : (precision == TTSB_PRECISION_FP16 ? 1 : 0);      // 3: split-fp16 (test hook)
-  pack_umma_weights(p.data(), k, Cin, Cout, ldw, wfmt, pb, cin_pad, cout_pad);
+  // as the engine: FP32 = tcgen05 with split-fp16 operands (the FFMA kernel where the shape is unsupported), FP32_FFMA = CUDA cores
+  const int wfmt = precision == TTSB_PRECISION_FP32 ? 2 : (precision == TTSB_PRECISION_FP16 ? 1 : 0);
+  float wscale = 0.f;
+  pack_umma_weights(p.data(), k, Cin, Cout, ldw, wfmt, pb, cin_pad, cout_pad, &wscale);
   float* dw = (float*)e.arena.alloc(sizeof(float) * p.size());
   uint16_t* dwb = (uint16_t*)e.arena.alloc(sizeof(uint16_t) * std::max<size_t>(pb.size(), 8));
   float* db = bias ? (float*)e.arena.alloc(sizeof(float) * Cout) : nullptr;
@@ -344,8 +360,13 @@ int ttsb_op_conv1d(ttsb_engine* h, const float* x, const float* w, const float* 
   a.x = x; a.ldx = Cin; a.w = dw; a.ldw = ldw; a.wb = pb.empty() ? nullptr : dwb; a.wfmt = wfmt; a.cin_pad = cin_pad; a.cout_pad = cout_pad; a.bias = db;
   a.y = y; a.ldy = Cout; a.Cin = Cin; a.Cout = Cout; a.k = k; a.dil = dilation; a.pad = (k * dilation - dilation) / 2; a.stride = 1;
   a.out_scale = 1.f; a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
-  const bool tensor = precision != TTSB_PRECISION_FP32;
-  if (tensor && !conv_umma_supported(a)) { set_error("op_conv1d: shape not supported by the tcgen05 kernel"); return TTSB_E_INVALID; }
+  a.split_wscale = wscale; a.sat = wfmt == 2 ? e.d_sat : nullptr;
+  bool tensor = precision != TTSB_PRECISION_FP32_FFMA;
+  if (tensor && !conv_umma_supported(a)) {
+    if (precision != TTSB_PRECISION_FP32) { set_error("op_conv1d: shape not supported by the tcgen05 kernel"); return TTSB_E_INVALID; }
+    tensor = false;
+  }
+  if (!tensor) { a.wb = nullptr; a.wfmt = 0; a.sat = nullptr; }
   if (reps < 1) reps = 1;
   OpTimer tm(e, ms);
   CKA(tm.start());
@@ -356,10 +377,10 @@ int ttsb_op_conv1d(ttsb_engine* h, const float* x, const float* w, const float* 
   if (ms) *ms /= (float)reps;
   CKA(cudaStreamSynchronize(e.stream));
   return TTSB_OK;
-}
+} GUARD_END("op_conv1d")
 
 int ttsb_op_bilstm(ttsb_engine* h, const float* x, int In, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                   const int32_t* row_offsets, int B, float* y, float* ms) {
+                   const int32_t* row_offsets, int B, float* y, float* ms) try {
   if (!h || !x || !w_ih || !w_hh || !b_ih || !b_hh || !row_offsets || B <= 0 || !y || In <= 0 || (In & 3)) { set_error("op_bilstm: bad arguments"); return TTSB_E_INVALID; }
   Engine& e = h->e;
   CKA(cudaSetDevice(e.device));
@@ -399,6 +420,6 @@ int ttsb_op_bilstm(ttsb_engine* h, const float* x, int In, const float* w_ih, co
   CKA(tm.stop());
   CKA(cudaStreamSynchronize(e.stream));
   return TTSB_OK;
-}
+} GUARD_END("op_bilstm")
 
 }  // extern "C"

@@ -383,6 +383,9 @@ struct Tw20 {                               // cos / sin(2 pi i / 20) as compile
   __host__ __device__ static constexpr float w(int m) { return 0.5f * (1.0f - c(m)); }   // periodic Hann(20)
 };
 
+// PRECISE: expf / sinf / sincosf instead of the fast intrinsics, whose absolute error grows with |x| (conv_post's log-magnitude and
+// phase logits are unbounded): the strict fp32 tier uses it, the 16-bit operand modes keep the intrinsics
+template <bool PRECISE>
 __global__ void __launch_bounds__(IS_FPB + 32) istft_kernel(const float* __restrict__ cp, int ld, float* __restrict__ audio, const Seg* __restrict__ segs) {
   __shared__ float fr_out[(IS_FPB + IS_HALO) * IS_LD];
   const Seg seg = segs[blockIdx.y];        // in: frames (120F+1), out: samples (600F)
@@ -400,9 +403,10 @@ __global__ void __launch_bounds__(IS_FPB + 32) istft_kernel(const float* __restr
       float re[11], im[11];
 #pragma unroll
       for (int k = 0; k <= 10; ++k) {
-        const float mag = __expf(x[k]);
+        const float mag = PRECISE ? expf(x[k]) : __expf(x[k]);
         float sn, cs;
-        __sincosf(__sinf(x[11 + k]), &sn, &cs);
+        if (PRECISE) sincosf(sinf(x[11 + k]), &sn, &cs);
+        else __sincosf(__sinf(x[11 + k]), &sn, &cs);
         re[k] = mag * cs; im[k] = mag * sn;
       }
       // x[m] = (X0 + (-1)^m X10 + 2 sum_{k=1..9} (Re_k cos t - Im_k sin t)) / 20,  t = 2 pi k m / 20.
@@ -537,14 +541,15 @@ cudaError_t launch_up_add(const float* up, int ldu, int up_row_shift, int reflec
   up_add_kernel<<<grid, 128, 0, s>>>(up, ldu, up_row_shift, reflect, xs, ldxs, y, ldy, C, segs, ostats, ld_ostats);
   return launched();
 }
-cudaError_t launch_istft(const float* cp, int ld, float* audio, const Seg* segs, int nseg, int max_frames, cudaStream_t s) {
+cudaError_t launch_istft(const float* cp, int ld, float* audio, const Seg* segs, int nseg, int max_frames, bool precise, cudaStream_t s) {
   if (nseg <= 0 || max_frames <= 1) return cudaSuccess;
   cudaError_t e = ensure_tables();
   if (e != cudaSuccess) return e;
   if (ld < 24 || (ld & 3) || (reinterpret_cast<uintptr_t>(cp) & 15)) return cudaErrorInvalidValue;   // rows are read as six float4
   const int max_samples = 5 * (max_frames - 1) + 10;       // padded-signal samples that matter
   dim3 grid((max_samples + 5 * IS_FPB - 1) / (5 * IS_FPB), nseg);
-  istft_kernel<<<grid, IS_FPB + 32, 0, s>>>(cp, ld, audio, segs);
+  if (precise) istft_kernel<true><<<grid, IS_FPB + 32, 0, s>>>(cp, ld, audio, segs);
+  else istft_kernel<false><<<grid, IS_FPB + 32, 0, s>>>(cp, ld, audio, segs);
   return launched();
 }
 

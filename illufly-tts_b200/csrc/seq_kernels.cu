@@ -296,8 +296,10 @@ __global__ void duration_kernel(const float* __restrict__ logits, int ld, int nb
   const float d = __fdiv_rn(s, speeds[row2seg[row]]);
   duration[row] = d;
   const float r = rintf(d);            // round half to even == torch.round
-  int n = (int)r;
-  if (n < 1) n = 1;
+  // sum of 50 sigmoids / speed: at most 50 000 with the speeds begin() admits; the upper clamp only guards the scan against a
+  // NaN / inf logit (float -> int conversion saturates), it never changes a representable duration
+  int n = (r >= 65536.f) ? 65536 : (int)r;
+  if (!(r >= 1.f)) n = 1;
   pred_dur[row] = n;
 }
 

@@ -16,9 +16,10 @@ import torch
 
 from . import _lib
 
-PRECISION_FP32 = 0
+PRECISION_FP32 = 0          # the strict tier: tcgen05 with split-fp16 operands (fp32-class products) on every convolution
 PRECISION_BF16 = 1
 PRECISION_FP16 = 2
+PRECISION_FP32_FFMA = 3     # CUDA-core fp32 everywhere: the arithmetic reference of the strict tier
 CHECKPOINT_MODULES = ("bert", "bert_encoder", "predictor", "decoder", "text_encoder")
 
 
@@ -117,7 +118,8 @@ class Engine:
         _lib.check(self._lib.ttsb_engine_last_step_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
-    PROFILE_CATEGORIES = ("conv_tensor", "conv_fp32", "lstm", "istft", "upsample_add", "gather", "attention", "layernorm", "harmonic_source")
+    PROFILE_CATEGORIES = ("conv_tensor", "conv_fp32", "lstm", "istft", "upsample_add", "gather", "attention", "layernorm", "harmonic_source",
+                          "fp32_projections")
 
     @_serialised
     def profile(self, on: bool = True):

@@ -40,17 +40,24 @@ enum {
   TTSB_E_CUDA = -2,      /* a CUDA runtime call or kernel launch failed                */
   TTSB_E_STATE = -3,     /* call order violated (e.g. finish() without begin())        */
   TTSB_E_NOMEM = -4,     /* workspace could not be allocated                           */
-  TTSB_E_TOO_LONG = -5   /* an utterance exceeds 512 tokens (ALBERT positions; kokoro asserts the same) */
+  TTSB_E_TOO_LONG = -5,  /* an utterance exceeds 512 tokens (ALBERT positions; kokoro asserts the same), or the batch
+                            needs more frames than a call can address */
+  TTSB_E_RANGE = -6      /* an operand of the split-fp16 (fp32-class) tensor-core path left fp16's range: the result would
+                            not be fp32-class; rerun with TTSB_PRECISION_FP32_FFMA */
 };
 
-/* arithmetic of the frame side (decoder + vocoder).  The text side, which decides the integer durations, keeps fp32
- * accuracy in every mode: fp32 FFMA in TTSB_PRECISION_FP32, tcgen05 with split-fp16 operands (x = hi + lo, three MMAs per
- * K step, fp32-class products) in the two tensor modes; pred_dur is bit-exact against the fp32 reference in all three. */
+/* arithmetic of the convolutions / projections.  The text side, which decides the integer durations, has fp32-class
+ * accuracy in every mode (tcgen05 with split-fp16 operands: x = hi + lo, three MMAs per K step, fp32 accumulation; or fp32
+ * FFMA in TTSB_PRECISION_FP32_FFMA); pred_dur is bit-exact against the fp32 reference in all four.  The modes differ in the
+ * frame side (decoder + vocoder): */
 enum {
-  TTSB_PRECISION_FP32 = 0,   /* CUDA-core fp32 everywhere: waveform within 1e-3 max-abs of the fp32 reference   */
+  TTSB_PRECISION_FP32 = 0,   /* the strict tier: every convolution on tcgen05 with split-fp16 operands (fp32-class
+                                products): waveform within 1e-3 max-abs of the fp32 reference                      */
   TTSB_PRECISION_BF16 = 1,   /* tcgen05 (kind::f16) bf16 operands, fp32 accumulate/statistics                    */
-  TTSB_PRECISION_FP16 = 2    /* tcgen05 (kind::f16) fp16 operands (saturating), fp32 accumulate/statistics: same
+  TTSB_PRECISION_FP16 = 2,   /* tcgen05 (kind::f16) fp16 operands (saturating), fp32 accumulate/statistics: same
                                 instruction and rate as bf16, 3 more mantissa bits (~ +18 dB SNR)                */
+  TTSB_PRECISION_FP32_FFMA = 3 /* CUDA-core fp32 FFMA everywhere: the arithmetic reference of the strict tier (tests), and
+                                the mode for checkpoints whose activations leave the split path's range (TTSB_E_RANGE) */
 };
 
 enum {
@@ -90,7 +97,8 @@ TTSB_API int64_t ttsb_engine_launch_count(ttsb_engine* e);
 TTSB_API int ttsb_engine_last_step_ms(ttsb_engine* e, float* ms);
 /* per-kernel-category CUDA-event timing of the next steps (bench.py's roofline): category 0 tcgen05 conv, 1 fp32 conv,
  * 2 LSTM recurrence, 3 iSTFT, 4 upsample-add (elementwise), 5 length-regulation gather, 6 attention, 7 LayerNorm family (ALBERT
- * embedding LN, LN, AdaLayerNorm), 8 harmonic source (phase scan + SineGen/STFT).  Results are those of the last step. */
+ * embedding LN, LN, AdaLayerNorm), 8 harmonic source (phase scan + SineGen/STFT), 9 fp32 row projections (style -> AdaIN scales
+ * and shifts, F0_proj / N_proj).  Results are those of the last step. */
 TTSB_API int ttsb_engine_profile(ttsb_engine* e, int on);
 TTSB_API int ttsb_engine_profile_read(ttsb_engine* e, int category, double* ms, double* flops, double* bytes, int64_t* launches);
 

@@ -559,8 +559,9 @@ class KokoroOracle(nn.Module):
     @torch.no_grad()
     def forward_batch(self, ids_list: List[List[int]], ref_s: torch.Tensor, speeds: Optional[List[float]] = None,
                       noise: Optional[List[torch.Tensor]] = None, noise_seed: int = 0, want_taps: bool = False,
-                      stop_after_durations: bool = False) -> OracleOutput:
-        """``ids_list[b]`` already includes BOS/EOS zeros (kmodel.py:36-42)."""
+                      stop_after_durations: bool = False, tap_keys=None) -> OracleOutput:
+        """``ids_list[b]`` already includes BOS/EOS zeros (kmodel.py:36-42).  ``tap_keys``: keep only these taps (a batch-32
+        run with every generator stage kept is ~1 GB)."""
         B = len(ids_list)
         speeds = speeds or [1.0] * B
         if ref_s.dim() == 3:
@@ -599,6 +600,8 @@ class KokoroOracle(nn.Module):
             audio = self.decoder(asr, F0, N, ref_s[i: i + 1, :128], nz[None], taps).squeeze()
             if want_taps:
                 taps.update(dict(d=d[i, :L], en=en[0], F0=F0[0], N=N[0], t_en=t_en[0], asr=asr[0]))
+                if tap_keys is not None:
+                    taps = {k: v for k, v in taps.items() if k in tap_keys}
                 out.taps.append(taps)
             out.audio.append(audio)
         return out

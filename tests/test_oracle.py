@@ -22,6 +22,13 @@ def test_param_counts(oracle):
     assert abs(got["text_encoder"] / 1e6 - 5.60) < 0.01
     assert abs(got["decoder"] / 1e6 - 53.29) < 0.02
     assert sum(got.values()) == 81_763_410
+    # SURVEY.md 8(c) quotes 81,777,868: that figure counts nn.Parameters with weight norm FOLDED (no weight_g: -32,154) and with the
+    # InstanceNorm affine weight/bias that kokoro's AdaIN1d creates but the checkpoint does not hold (+46,612); the checkpoint's own
+    # tensor count is the one above.  81,763,410 - 32,154 + 46,612 = 81,777,868.
+    all_params = sum(p.numel() for k in got for p in getattr(oracle, k).parameters())
+    weight_g = sum(p.numel() for k in got for n, p in getattr(oracle, k).state_dict().items() if n.endswith("weight_g"))
+    assert all_params - sum(got.values()) == 46_612 and weight_g == 32_154
+    assert all_params - weight_g == 81_777_868
 
 
 def test_checkpoint_layout(checkpoint):
