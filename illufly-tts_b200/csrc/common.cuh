@@ -73,6 +73,27 @@ struct LstmGroup {
 extern long long g_launches;
 inline cudaError_t launched(int n = 1) { __sync_fetch_and_add(&g_launches, (long long)n); return cudaGetLastError(); }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------------
+// A step is ~300 launches on one stream, most of them tens of microseconds long: the gap between two launches and the prologue of
+// a persistent kernel (TMEM allocation, barrier initialisation, the first weight stages) are a visible share of a short step.
+// Kernels launched through launch_pdl() may start while the previous kernel on the stream is still draining; they must call
+// pdl_wait() before they touch anything an earlier kernel wrote (it returns once the previous kernel has completed and flushed;
+// completion is transitive because EVERY CTA of every such kernel executes pdl_wait() before it exits), and they call
+// pdl_trigger() at their top so that the next kernel's launch is not held back either.  TTSB_NO_PDL=1 launches them the plain way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- kernel launchers (each returns the launch error) -------------------------------------------------
 cudaError_t launch_conv_simt(const ConvArgs& a, cudaStream_t s);
 cudaError_t launch_rowdot(const float* x, int ldx, int rows, int C, const float* w, int ldw, const float* bias, float* y, int ldy,

@@ -60,6 +60,7 @@ struct UArgs {
   Plan p;
   long long* prof;   // optional [grid][16] cycle counters per role (TTSB_UMMA_PROF), else null
   const uint8_t* xpack;   // pre-packed operand slabs [tile][K chunk][slab image] (pack_split_kernel), else null
+  int l2pf;    // row loader asks the L2 for the next item's inputs (TTSB_L2PF bit 0; default off: measured slower on these layers)
   int dbg;     // TTSB_UMMA_DBG (timing experiments only, results become garbage): 1 = producers skip global loads,
                // 2 = epilogue skips global traffic, 4 = no MMA issue; applied to the Snake-prologue variants only
 };
@@ -68,14 +69,12 @@ struct UArgs {
 // group is complete, no activation.  y = (acc * acs + bias [+ res]) [* os] [+ y_old]; returns the lane's partial column sums.
 // RES / SCALE / ACC are compile-time so that each launch runs one short loop (4 epilogue warps are issue-latency bound:
 // ncu shows ~8 cycles per instruction per warp, so the instruction count per element is what matters).
+// r4: the residual rows of this chunk, requested by the caller at the TOP of the chunk - before the TMEM load and the staging
+// writes, so that their latency overlaps that work (the L2 prefetch of the row loader has made them L2 hits by then).
 template <bool RES, bool SCALE, bool ACC>
 __device__ __forceinline__ void epi_chunk_fast(const float* __restrict__ stg, int lane, float acs, float os, const float4 b4, float* __restrict__ yb,
-                                               size_t ystep, const float* __restrict__ rb, size_t rstep, float (&ps)[4], float (&pq)[4]) {
-  float4 r4[8], y4[8];
-  if (RES) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(rb + i * rstep);
-  }
+                                               size_t ystep, const float4 (&r4)[8], float (&ps)[4], float (&pq)[4]) {
+  float4 y4[8];
   if (ACC) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) y4[i] = *reinterpret_cast<const float4*>(yb + i * ystep);
@@ -131,17 +130,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
   if (tid == 0) {
     for (int s = 0; s < MAXSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_slab_full(b), u.xpack ? 1 : NPROD); mbar_init(bar_slab_empty(b), 1);
-      mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), NEPI);
+      // one elected lane arrives for its warp (after __syncwarp): 256 lanes arriving on one shared-memory word serialise
+      mbar_init(bar_slab_full(b), u.xpack ? 1 : NPROD / 32); mbar_init(bar_slab_empty(b), 1);
+      mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), NEPI / 32);
     }
-    for (int b = 0; b < MAXRAW; ++b) { mbar_init(bar_raw_full(b), 1); mbar_init(bar_raw_empty(b), NPROD); }
+    for (int b = 0; b < MAXRAW; ++b) { mbar_init(bar_raw_full(b), 1); mbar_init(bar_raw_empty(b), NPROD / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int c = tid; c < 2048; c += NTHREADS) s_sum[c] = 0.0;
+  pdl_trigger();                                   // the next kernel on the stream may start its own prologue
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // everything above ran under the previous kernel's tail; the weight loader (static data) keeps going, every other role waits here
+  // for the previous kernel's results (activations, statistics, residuals, packed operand images)
+  if (warp != NPW) pdl_wait();
 
   const int nwst = pl.KS / KCH;                      // weight stages per (slab, tap)
   const uint32_t slab0 = smem_u32(smem + pl.off_slab);
@@ -349,7 +353,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             }
             if (hasa) xform_store(ra, a0, a1);
             if (hasb) xform_store(rb, b0, b1);
-            mbar_arrive(bar_raw_empty(rslot));      // this thread is done reading the slot
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_raw_empty(rslot));      // this warp is done reading the slot
             if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
           }
         } else if (c0 >= p.Cin) {                      // padding channels of the last K chunk: zeros, no loads
@@ -386,7 +391,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           }
         }
         fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
-        mbar_arrive(bar_slab_full(b));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_slab_full(b));
       }
     }
     if (WFMT == 2 && p.sat && satm * SPLIT_SA > 65504.f) atomicAdd(p.sat, 1u);
@@ -483,11 +489,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       }
     }
   } else if (warp == NPW + 2 + NEPI / 32) {
-    // =================== row loader: fp32 activation rows -> raw ring (bulk-copy engine) ===================
-    if (pl.nraw > 0) {
+    // =================== row loader: L2 prefetch one item ahead; fp32 activation rows -> raw ring (bulk-copy engine) ==========
+    {
       uint32_t rslot = 0, rphase = 0;
       const int nch = (pl.SR + pl.rch - 1) / pl.rch;
+      // One item ahead, ask the L2 for what the producers (activation rows or packed operand images) and the epilogue (residual
+      // rows, the old output when it is accumulated) will read: their requests then find the lines in L2 instead of paying the
+      // HBM latency with the few KB each role can keep in flight.
+      auto prefetch_item = [&](int item) {
+        if (item >= item1 || lane != 0 || !u.l2pf) return;
+        const Tile tl = p.tiles[item % p.ntiles];
+        const Seg sg = p.segs[tl.seg];
+        auto pf = [&](const void* ptr, size_t bytes) {
+          const uint8_t* b = reinterpret_cast<const uint8_t*>(ptr);
+          const size_t lead = (16 - (reinterpret_cast<uintptr_t>(b) & 15)) & 15;      // 16-byte aligned, a multiple of 16
+          if (bytes <= lead) return;
+          b += lead; bytes = (bytes - lead) & ~size_t(15);
+          for (size_t o = 0; o < bytes; o += 16384) prefetch_l2(b + o, (uint32_t)(bytes - o < 16384 ? bytes - o : 16384));
+        };
+        if (u.xpack) {
+          pf(u.xpack + (size_t)(item % p.ntiles) * pl.nsc * pl.slab_bytes, (size_t)pl.nsc * pl.slab_bytes);
+        } else {
+          int lo = (tl.t0 - p.pad) >> p.in_shr, hi = ((tl.t0 - p.pad + pl.SR - 1) >> p.in_shr) + 1;
+          lo = max(lo, 0); hi = min(hi, sg.in_len);
+          if (hi > lo) pf(p.x + (size_t)(sg.in_off + lo) * p.ldx, (size_t)(hi - lo) * p.ldx * 4);
+        }
+        const int nr = min(BM, sg.out_len - tl.t0);
+        const int n0 = (item / p.ntiles) * pl.BN;
+        if (nr > 0 && p.res) {
+          if (p.ldr <= pl.BN) pf(p.res + (size_t)(sg.out_off + tl.t0) * p.ldr, (size_t)nr * p.ldr * 4);      // whole rows
+          else for (int r = 0; r < nr; ++r) pf(p.res + (size_t)(sg.out_off + tl.t0 + r) * p.ldr + n0, (size_t)min(pl.BN, p.Cout - n0) * 4);
+        }
+        if (nr > 0 && p.accumulate && p.ldy <= pl.BN) pf(p.y + (size_t)(sg.out_off + tl.t0) * p.ldy, (size_t)nr * p.ldy * 4);
+      };
+      prefetch_item(item0);
       for (int item = item0; item < item1; ++item) {
+        prefetch_item(item + 1);
+        if (pl.nraw == 0) continue;
         const Tile tile = p.tiles[item % p.ntiles];
         const Seg seg = p.segs[tile.seg];
         const int row_lo = tile.t0 - p.pad;
@@ -534,12 +572,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       const Seg seg = p.segs[tile.seg];
       const int n0 = nt * pl.BN;
       const uint32_t slot = n & 1u;
+      const bool tile_fast = tile.t0 + BM <= seg.out_len && p.act == ACT_NONE && !(u.dbg & 2);
+      const size_t row0 = (size_t)(seg.out_off + tile.t0 + q * 32 + (lane >> 3));
+      const size_t ystep = (size_t)4 * p.ldy, rstep = (size_t)4 * p.ldr;
       mbar_wait_t(bar_acc_full(slot), (n >> 1) & 1u, tw_full);
       tc_fence_after();
       const uint32_t tacc = tmem_base + slot * (uint32_t)pl.acc_cols + ((uint32_t)(q * 32) << 16);
       for (int chunk = 0; chunk < nchunk; ++chunk) {
         const int c0 = chunk * 32;
         const int co = n0 + c0 + cc;
+        // residual rows of this chunk: requested before the TMEM load and the staging writes below (they do not depend on them)
+        float4 r4[8];
+        const bool chunk_fast = tile_fast && co + 3 < p.Cout;
+        if (p.res && chunk_fast) {
+          const float* rb = p.res + row0 * p.ldr + co;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(rb + i * rstep);
+        }
         uint32_t v[32];
         tmem_ld32(tacc + (uint32_t)c0, v);
         if (WFMT == 2) {
@@ -550,7 +599,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         }
         if (chunk == nchunk - 1) {                     // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
-          mbar_arrive(bar_acc_empty(slot));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty(slot));      // one arrival per warp (128 lanes on one word serialise)
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -562,23 +612,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
         const bool colok = co < p.Cout && !(u.dbg & 2);
         const bool full4 = co + 3 < p.Cout;
-        if (colok && full4 && tile.t0 + BM <= seg.out_len && p.act == ACT_NONE) {
+        if (colok && full4 && tile_fast) {
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + co);
-          const size_t row0 = (size_t)(seg.out_off + tile.t0 + q * 32 + (lane >> 3));
           float* yb = p.y + row0 * p.ldy + co;
-          const size_t ystep = (size_t)4 * p.ldy, rstep = (size_t)4 * p.ldr;
-          const float* rb = p.res ? p.res + row0 * p.ldr + co : nullptr;
           const bool sc = p.out_scale != 1.0f;
-          if (p.res && p.accumulate) epi_chunk_fast<true, true, true>(stg, lane, acs, p.out_scale, b4, yb, ystep, rb, rstep, ps, pq);
-          else if (p.res && sc) epi_chunk_fast<true, true, false>(stg, lane, acs, p.out_scale, b4, yb, ystep, rb, rstep, ps, pq);
-          else if (p.res) epi_chunk_fast<true, false, false>(stg, lane, acs, 1.f, b4, yb, ystep, rb, rstep, ps, pq);
-          else if (p.accumulate) epi_chunk_fast<false, true, true>(stg, lane, acs, p.out_scale, b4, yb, ystep, rb, rstep, ps, pq);
-          else if (sc) epi_chunk_fast<false, true, false>(stg, lane, acs, p.out_scale, b4, yb, ystep, rb, rstep, ps, pq);
-          else epi_chunk_fast<false, false, false>(stg, lane, acs, 1.f, b4, yb, ystep, rb, rstep, ps, pq);
+          if (p.res && p.accumulate) epi_chunk_fast<true, true, true>(stg, lane, acs, p.out_scale, b4, yb, ystep, r4, ps, pq);
+          else if (p.res && sc) epi_chunk_fast<true, true, false>(stg, lane, acs, p.out_scale, b4, yb, ystep, r4, ps, pq);
+          else if (p.res) epi_chunk_fast<true, false, false>(stg, lane, acs, 1.f, b4, yb, ystep, r4, ps, pq);
+          else if (p.accumulate) epi_chunk_fast<false, true, true>(stg, lane, acs, p.out_scale, b4, yb, ystep, r4, ps, pq);
+          else if (sc) epi_chunk_fast<false, true, false>(stg, lane, acs, p.out_scale, b4, yb, ystep, r4, ps, pq);
+          else epi_chunk_fast<false, false, false>(stg, lane, acs, 1.f, b4, yb, ystep, r4, ps, pq);
         } else if (colok && full4) {
           // all global reads of the chunk first (res / y may alias the output, so the compiler cannot hoist them itself)
-          float4 r4[8], y4[8];
+          float4 y4[8];
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + co);
 #pragma unroll
@@ -687,6 +734,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
 template <int PRO, int WFMT>
 __global__ void __launch_bounds__(256) pack_act_kernel(const ConvArgs p, int KS, int nsc, int SR, uint32_t slab_bytes, uint8_t* __restrict__ out) {
   __shared__ float s_par[5][128];
+  pdl_trigger();
+  pdl_wait();                                      // the activations (and the segment tables of the step) come from earlier work
   const Tile tile = p.tiles[blockIdx.x];
   const Seg seg = p.segs[tile.seg];
   const int sc = blockIdx.y;
@@ -927,6 +976,8 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   static int dbg = -1;
   if (dbg < 0) { const char* ev = getenv("TTSB_UMMA_DBG"); dbg = ev ? atoi(ev) : 0; }
   u.dbg = a.pro == PRO_ADAIN_SNAKE ? dbg : 0;
+  static const int l2pf = getenv("TTSB_L2PF") ? atoi(getenv("TTSB_L2PF")) : 0;
+  u.l2pf = l2pf & 1;
   static int prof_on = -1;
   static long long* prof_buf = nullptr;
   if (prof_on < 0) {
@@ -944,8 +995,10 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
         {pack_act_kernel<0, 0>, pack_act_kernel<0, 1>, pack_act_kernel<0, 2>}, {pack_act_kernel<1, 0>, pack_act_kernel<1, 1>, pack_act_kernel<1, 2>},
         {pack_act_kernel<2, 0>, pack_act_kernel<2, 1>, pack_act_kernel<2, 2>}, {pack_act_kernel<3, 0>, pack_act_kernel<3, 1>, pack_act_kernel<3, 2>}};
     const int pack_items = (u.p.KS >> 3) * u.p.SR;
-    ptable[a.pro][a.wfmt]<<<dim3(a.ntiles, u.p.nsc, (pack_items + 255) / 256), 256, 0, s>>>(u.a, u.p.KS, u.p.nsc, u.p.SR, u.p.slab_bytes, a.xpack);
-    cudaError_t e = launched();
+    cudaError_t e = launch_pdl(ptable[a.pro][a.wfmt], dim3(a.ntiles, u.p.nsc, (pack_items + 255) / 256), dim3(256), 0, s, u.a, u.p.KS, u.p.nsc, u.p.SR,
+                               u.p.slab_bytes, a.xpack);
+    if (e != cudaSuccess) return e;
+    e = launched();
     if (e != cudaSuccess) return e;
     u.xpack = a.xpack;
     u.p.nraw = 0;                     // no row ring in this mode
@@ -959,7 +1012,10 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
     if (!pe0) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
     cudaEventRecord(pe0, s);
   }
-  kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
+  {
+    cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(NTHREADS), u.p.smem_bytes, s, u);
+    if (e != cudaSuccess) return e;
+  }
   if (prof_on) cudaEventRecord(pe1, s);
   if (prof_on) {      // diagnostic mode: synchronous, prints the mean cycle split of the roles for every launch
     static long long host[16 * 256];

@@ -59,40 +59,69 @@ struct WArgs {
   ConvArgs a;
   WPlan p;
   long long* prof;
+  int l2pf;            // row loader asks the L2 for the next tile's rows (TTSB_L2PF bit 1; default off: measured slower, the prefetch doubles the request traffic of a throughput-bound memory system)
 };
 
-// eight rows of one 32-column chunk: y[row0 + i][c] for i = I0 .. I0+7, one output channel c per thread
-template <bool RES, bool SCALE, bool ACC, bool YH>
-__device__ __forceinline__ void epi_rows8(const uint32_t (&v)[32], const int i0, const int nvalid, const float bias, const float os, float* __restrict__ yb,
-                                          __half* __restrict__ yh, const size_t ldy, const float* __restrict__ rb, const size_t ldr, float& ps, float& pq) {
-  float r[8], yo[8];
-  if (RES) {
+// The epilogue of one tile for one warp: 128 time steps of this thread's output channel.
+// The residual (and old-output) rows come in through a ROLLING WINDOW of W registers: row i + W is requested the moment row i has
+// been consumed, so every thread has W loads in flight all the time (a warp: W x 128 B).  Measured on B200: with 8 loads per batch
+// and nothing overlapped the epilogue ran at the latency of 16 memory round trips per tile (30 k cycles against 11 k of tensor
+// time); with units of 16 rows requested one unit ahead, at 8 x ~2.2 k cycles (the load latency under this kernel's own traffic).
+// FULL: the half tile lies inside the utterance - straight-line code; otherwise rows past the utterance's end are predicated.
+//   y = (acc + bias [+ res]) [* os] [+ y_old]; dsum / dsq += this thread's sum / sum of squares of what it stored
+template <bool RES, bool SCALE, bool ACC, bool YH, bool FULL>
+__device__ __forceinline__ void epi_tile(const uint32_t tacc, const int nv, const float bias, const float os, float* __restrict__ yb, __half* __restrict__ yh,
+                                         const float* __restrict__ rb, const uint32_t bar_empty, const int lane, double& dsum, double& dsq) {
+  constexpr size_t ldy = CH, ldr = CH;             // rows of y and res are whole channel rows (conv_umma_wa_supported): the row offsets
+                                                   // below are immediates of the load / store instructions, not address registers
+  constexpr int W = ACC ? 16 : 32;                 // window depth per stream (two streams when the old output is read too)
+  float rw[W], yw[ACC ? W : 1];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = (i0 + i < nvalid) ? rb[(size_t)(i0 + i) * ldr] : 0.f;
+  for (int i = 0; i < W; ++i) {
+    if (RES) rw[i] = (FULL || i < nv) ? rb[(size_t)i * ldr] : 0.f;
+    if (ACC) yw[i] = (FULL || i < nv) ? yb[(size_t)i * ldy] : 0.f;
   }
-  if (ACC) {
+  uint32_t v[16];
+  float ps = 0.f, pq = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) yo[i] = (i0 + i < nvalid) ? yb[(size_t)(i0 + i) * ldy] : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i0 + i < nvalid) {
-      float o = __uint_as_float(v[i0 + i]) + bias;
-      if (RES) o += r[i];
-      if (SCALE && ACC) o = fmaf(o, os, yo[i]);
-      else if (SCALE) o *= os;
-      else if (ACC) o += yo[i];
-      if (YH) {
-        const __half h = __float2half_rn(fminf(fmaxf(o, -65504.f), 65504.f));
-        yh[(size_t)(i0 + i) * ldy] = h;
-        o = __half2float(h);                      // the statistics describe what the consumer will read
-      } else {
-        yb[(size_t)(i0 + i) * ldy] = o;
+  for (int i = 0; i < 128; ++i) {
+    if (i % 16 == 0) {
+      tmem_ld16(tacc + (uint32_t)i, v);
+      if (i == 112) {                              // last read of this accumulator: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty);
       }
-      ps += o;
-      pq = fmaf(o, o, pq);
     }
+    const bool ok = FULL || i < nv;
+    float o = __uint_as_float(v[i % 16]) + bias;
+    if (RES) o += rw[i % W];
+    if (SCALE && ACC) o = fmaf(o, os, yw[i % W]);
+    else if (SCALE) o *= os;
+    else if (ACC) o += yw[i % W];
+    if (i + W < 128) {                             // refill the slots just consumed: row i + W
+      if (RES) rw[i % W] = (FULL || i + W < nv) ? rb[(size_t)(i + W) * ldr] : 0.f;
+      if (ACC) yw[i % W] = (FULL || i + W < nv) ? yb[(size_t)(i + W) * ldy] : 0.f;
+    }
+    if (YH) {
+      const __half h = __float2half_rn(fminf(fmaxf(o, -65504.f), 65504.f));
+      if (ok) yh[(size_t)i * ldy] = h;
+      o = __half2float(h);                          // the statistics describe what the consumer will read
+    } else {
+      if (ok) yb[(size_t)i * ldy] = o;
+    }
+    if (!FULL) o = ok ? o : 0.f;
+    ps += o;
+    pq = fmaf(o, o, pq);
+    if (i % 16 == 15) { dsum += (double)ps; dsq += (double)pq; ps = 0.f; pq = 0.f; }
   }
+}
+
+template <bool RES, bool SCALE, bool ACC, bool YH>
+__device__ __forceinline__ void epi_tile_any(const uint32_t tacc, const int nv, const float bias, const float os, float* yb, __half* yh, const float* rb,
+                                             const uint32_t bar_empty, const int lane, double& dsum, double& dsq) {
+  if (nv >= 128) epi_tile<RES, SCALE, ACC, YH, true>(tacc, 128, bias, os, yb, yh, rb, bar_empty, lane, dsum, dsq);
+  else epi_tile<RES, SCALE, ACC, YH, false>(tacc, nv, bias, os, yb, yh, rb, bar_empty, lane, dsum, dsq);
 }
 
 template <int WFMT, bool XH, bool YH>
@@ -123,16 +152,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
   if (tid == 0) {
     for (int s = 0; s < MAXSTAGE; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(bar_slab_full(b), NPROD); mbar_init(bar_slab_empty(b), 1);
-      mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), NEPI);
+      // one elected lane arrives for its warp (after __syncwarp): 256 lanes arriving on one shared-memory word serialise
+      mbar_init(bar_slab_full(b), NPROD / 32); mbar_init(bar_slab_empty(b), 1);
+      mbar_init(bar_acc_full(b), 1); mbar_init(bar_acc_empty(b), NEPI / 32);
     }
-    for (int b = 0; b < MAXRAW; ++b) { mbar_init(bar_raw_full(b), 1); mbar_init(bar_raw_empty(b), NPROD); }
+    for (int b = 0; b < MAXRAW; ++b) { mbar_init(bar_raw_full(b), 1); mbar_init(bar_raw_empty(b), NPROD / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  pdl_trigger();                                   // the next kernel on the stream may start its own prologue
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  // the weight loader (static data) starts under the previous kernel's tail; every other role waits for that kernel's results
+  if (warp != 8) pdl_wait();
 
   const uint32_t slab0 = smem_u32(smem + pl.off_slab);
   const uint32_t w0 = smem_u32(smem + pl.off_w);
@@ -218,7 +251,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
           }
           if (hasa) xform_store(slab, ra, va);
           if (hasb) xform_store(slab, rb, vb);
-          mbar_arrive(bar_raw_empty(rslot));      // this thread is done reading the slot
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_raw_empty(rslot));      // this warp is done reading the slot
           if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
         }
       } else {
@@ -240,7 +274,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
         }
       }
       fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
-      mbar_arrive(bar_slab_full(b));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_slab_full(b));
     }
     if (u.prof && tid == 0) { u.prof[blockIdx.x * 16 + 0] = clock64() - t_start; u.prof[blockIdx.x * 16 + 1] = t_wait; }
   } else if (warp == 8) {
@@ -306,9 +341,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     }
   } else if (warp == 18) {
     // =================== row loader: raw activation rows -> ring (bulk-copy engine) ===================
-    if (pl.nraw > 0 && lane == 0) {
+    if (lane == 0) {
       uint32_t rslot = 0, rphase = 0;
+      // The ring holds 32 KB: at HBM latency that is ~20 GB/s per SM, less than a tile needs.  One tile ahead, the loader asks the
+      // L2 for the rows the ring (and the epilogue's residual loads) will want next, so that those requests are L2 hits.
+      auto prefetch_tile = [&](int item) {
+        if (item >= item1 || !u.l2pf) return;
+        const Tile tl = p.tiles[item];
+        const Seg sg = p.segs[tl.seg];
+        int lo = tl.t0 - p.pad, hi = lo + SR;
+        lo = max(lo, 0); hi = min(hi, sg.in_len);
+        if (hi > lo) {
+          const uint8_t* src = xbytes + (size_t)(sg.in_off + lo) * pl.row_bytes;
+          const uint32_t bytes = (uint32_t)(hi - lo) * pl.row_bytes;
+          for (uint32_t o = 0; o < bytes; o += 16384u) prefetch_l2(src + o, min(16384u, bytes - o));
+        }
+        if (p.res) {
+          const int nr = min(TN, sg.out_len - tl.t0);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.res + (size_t)(sg.out_off + tl.t0) * p.ldr);
+          const uint32_t bytes = (uint32_t)nr * (uint32_t)p.ldr * 4u;
+          for (uint32_t o = 0; o < bytes; o += 16384u) prefetch_l2(src + o, min(16384u, bytes - o));
+        }
+        if (p.accumulate && !YH) {                    // the running sum of the three parallel resblocks is read back too
+          const int nr = min(TN, sg.out_len - tl.t0);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.y + (size_t)(sg.out_off + tl.t0) * p.ldy);
+          const uint32_t bytes = (uint32_t)nr * (uint32_t)p.ldy * 4u;
+          for (uint32_t o = 0; o < bytes; o += 16384u) prefetch_l2(src + o, min(16384u, bytes - o));
+        }
+      };
+      prefetch_tile(item0);
       for (int item = item0; item < item1; ++item) {
+        prefetch_tile(item + 1);
+        if (pl.nraw == 0) continue;
         const Tile tile = p.tiles[item];
         const Seg seg = p.segs[tile.seg];
         const int row_lo = tile.t0 - p.pad;
@@ -331,7 +395,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     const int c = q * 32 + lane;                       // this thread's output channel
     const float bias = p.bias ? p.bias[c] : 0.f;
     const bool has_res = p.res != nullptr, acc = p.accumulate != 0, sc = p.out_scale != 1.0f;
-    const size_t ldy = (size_t)p.ldy, ldr = (size_t)p.ldr;
+    constexpr size_t ldy = CH, ldr = CH;
     double dsum = 0.0, dsq = 0.0;
     uint32_t n = 0;
     long long tw_full = 0;
@@ -344,35 +408,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
       tc_fence_after();
       const uint32_t tacc = tmem_base + slot * (uint32_t)TN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
       const int tbase = tile.t0 + half * 128;
-#pragma unroll 1
-      for (int chunk = 0; chunk < 4; ++chunk) {
-        uint32_t v[32];
-        tmem_ld32(tacc + (uint32_t)(chunk * 32), v);
-        if (chunk == 3) {                              // last read of this accumulator: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(bar_acc_empty(slot));
-        }
-        const int t0c = tbase + chunk * 32;
-        const int nvalid = min(32, seg.out_len - t0c);
-        if (nvalid > 0) {
-          const size_t row0 = (size_t)(seg.out_off + t0c);
-          float* yb = YH ? nullptr : p.y + row0 * ldy + c;
-          __half* yh = YH ? reinterpret_cast<__half*>(p.y) + row0 * ldy + c : nullptr;
-          const float* rb = has_res ? p.res + row0 * ldr + c : nullptr;
-          float ps = 0.f, pq = 0.f;
-#pragma unroll
-          for (int i0 = 0; i0 < 32; i0 += 8) {
-            if (YH) epi_rows8<false, false, false, true>(v, i0, nvalid, bias, 1.f, yb, yh, ldy, rb, ldr, ps, pq);
-            else if (has_res && acc) epi_rows8<true, true, true, false>(v, i0, nvalid, bias, p.out_scale, yb, yh, ldy, rb, ldr, ps, pq);
-            else if (has_res && sc) epi_rows8<true, true, false, false>(v, i0, nvalid, bias, p.out_scale, yb, yh, ldy, rb, ldr, ps, pq);
-            else if (has_res) epi_rows8<true, false, false, false>(v, i0, nvalid, bias, 1.f, yb, yh, ldy, rb, ldr, ps, pq);
-            else if (acc) epi_rows8<false, true, true, false>(v, i0, nvalid, bias, p.out_scale, yb, yh, ldy, rb, ldr, ps, pq);
-            else if (sc) epi_rows8<false, true, false, false>(v, i0, nvalid, bias, p.out_scale, yb, yh, ldy, rb, ldr, ps, pq);
-            else epi_rows8<false, false, false, false>(v, i0, nvalid, bias, 1.f, yb, yh, ldy, rb, ldr, ps, pq);
-          }
-          dsum += (double)ps; dsq += (double)pq;
-        }
-      }
+      const int nv = seg.out_len - tbase;              // rows of this half tile inside the utterance (<= 0: nothing to store)
+      const size_t row0 = (size_t)(seg.out_off + tbase);
+      float* yb = YH ? nullptr : p.y + row0 * ldy + c;
+      __half* yh = YH ? reinterpret_cast<__half*>(p.y) + row0 * ldy + c : nullptr;
+      const float* rb = has_res ? p.res + row0 * ldr + c : nullptr;
+      const uint32_t be = bar_acc_empty(slot);
+      if (YH) epi_tile_any<false, false, false, true>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
+      else if (has_res && acc) epi_tile_any<true, true, true, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
+      else if (has_res && sc) epi_tile_any<true, true, false, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
+      else epi_tile_any<true, false, false, false>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);      // fp32 output always has a residual (supported())
       if (p.ostats) {
         // flush this thread's running sums when the utterance changes or the CTA is done
         const bool flush = item + 1 >= item1 || p.tiles[item + 1].seg != tile.seg;
@@ -409,12 +454,13 @@ bool make_wplan(const ConvArgs& a, WPlan& pl) {
   if (off + pl.nstage * WSTAGE_BYTES > limit) return false;
   const uint32_t left = limit - off - pl.nstage * WSTAGE_BYTES;
   static const bool noring = getenv("TTSB_UMMA_NORING") != nullptr;
-  // a slot holds rps rows per producer thread: 16-KB slots (two rows in flight per thread) when at least three fit, else 8 KB
+  // a slot holds rps rows per producer thread: two rows (one barrier round trip per two rows: 16 KB of fp32, 8 KB of fp16) when
+  // at least two such slots fit, else one
   pl.rps = 2;
   pl.raw_bytes = (uint32_t)(2 * RPP) * pl.row_bytes;
-  if (!a.x_f16 && left / pl.raw_bytes < 3) { pl.rps = 1; pl.raw_bytes = (uint32_t)RPP * pl.row_bytes; }
+  if (left / pl.raw_bytes < 2) { pl.rps = 1; pl.raw_bytes = (uint32_t)RPP * pl.row_bytes; }
   pl.rch = pl.rps * RPP;
-  pl.nraw = (int)std::min<uint32_t>(left / pl.raw_bytes, a.x_f16 ? 6u : 4u);
+  pl.nraw = (int)std::min<uint32_t>(left / pl.raw_bytes, (uint32_t)MAXRAW);
   if (pl.nraw < 2 || noring) pl.nraw = 0;
   pl.nch = (pl.SR + pl.rch - 1) / pl.rch;
   pl.off_raw = off; off += pl.nraw * pl.raw_bytes;
@@ -432,10 +478,11 @@ bool g_attr_set_wa[64] = {false};
 
 bool conv_umma_wa_supported(const ConvArgs& a) {
   if (!a.wb || a.wfmt < 0 || a.wfmt > 1 || a.pro != PRO_ADAIN_SNAKE || a.stride != 1 || a.in_shr != 0 || a.act != ACT_NONE) return false;
-  if (a.tile_rows != TN || a.ldx != CH) return false;
+  if (a.tile_rows != TN || a.ldx != CH || a.ldy != CH || (a.res && a.ldr != CH)) return false;
   if (a.acc_scale != 0.f && a.acc_scale != 1.0f) return false;
   if (reinterpret_cast<uintptr_t>(a.x) & 15) return false;
   if (a.y_f16 && (a.res || a.accumulate || a.out_scale != 1.0f)) return false;
+  if (!a.y_f16 && !a.res) return false;        // the two shapes of an AdaINResBlock1: c1 (fp16 out, plain) and c2 (fp32 out + residual)
   if (!a.pstats || !a.gb || !a.alpha) return false;
   WPlan pl;
   return make_wplan(a, pl);
@@ -479,6 +526,8 @@ cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
     if (prof_on && cudaMalloc(&prof_buf, sizeof(long long) * 16 * 256) != cudaSuccess) prof_on = 0;
   }
   u.prof = prof_on ? prof_buf : nullptr;
+  static const int l2pf = getenv("TTSB_L2PF") ? atoi(getenv("TTSB_L2PF")) : 0;
+  u.l2pf = (l2pf >> 1) & 1;
   const int ncta = u.p.items < g_num_sms_wa[dev] ? u.p.items : g_num_sms_wa[dev];      // persistent: one CTA per SM
   u.p.per_cta = (u.p.items + ncta - 1) / ncta;
   const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
@@ -487,7 +536,10 @@ cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
     if (!pe0) { cudaEventCreate(&pe0); cudaEventCreate(&pe1); }
     cudaEventRecord(pe0, s);
   }
-  kernel<<<grid, NTHREADS, u.p.smem_bytes, s>>>(u);
+  {
+    cudaError_t e = launch_pdl(kernel, dim3(grid), dim3(NTHREADS), u.p.smem_bytes, s, u);
+    if (e != cudaSuccess) return e;
+  }
   if (prof_on) {      // diagnostic mode: synchronous, prints the mean cycle split of the roles for every launch
     cudaEventRecord(pe1, s);
     static long long host[16 * 256];

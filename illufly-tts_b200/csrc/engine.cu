@@ -20,6 +20,10 @@ constexpr int MAX_DUR_PER_TOKEN = 1 << 16;
 constexpr long long MAX_FRAMES_PER_CALL = 1000000;     // 6.9 hours of audio; the workspace (~0.6 MB per frame) gives out long before
 
 long long g_launches = 0;
+bool pdl_enabled() {
+  static const bool on = getenv("TTSB_NO_PDL") == nullptr;
+  return on;
+}
 static thread_local char g_err[1024] = "";
 const char* last_error() { return g_err; }
 void set_error(const char* fmt, ...) {
@@ -49,33 +53,54 @@ void set_error(const char* fmt, ...) {
 void Arena::release() {
   for (auto& c : chunks_) cudaFree(c.p);
   chunks_.clear();
+  cur_ = 0;
   total_used_ = 0;
 }
 void Arena::reset() {
   if (chunks_.size() > 1) {
-    size_t cap = 0;
-    for (auto& c : chunks_) cap += c.cap;
+    // the last step spilled into extra chunks: one allocation of the step's high-water mark (rounded up) replaces them
+    size_t cap = ((peak_ + (peak_ >> 3)) + (size_t(256) << 20) - 1) & ~((size_t(256) << 20) - 1);
     release();
     char* p = nullptr;
     if (cudaMalloc(&p, cap) == cudaSuccess) chunks_.push_back({p, cap, 0});
     else (void)cudaGetLastError();
   }
   for (auto& c : chunks_) c.off = 0;
+  cur_ = 0;
   total_used_ = 0;
+  peak_ = 0;
 }
 void* Arena::alloc(size_t bytes) {
   bytes = (bytes + 255) & ~size_t(255);
   if (bytes == 0) bytes = 256;
-  if (!chunks_.empty()) {
-    Chunk& c = chunks_.back();
-    if (c.off + bytes <= c.cap) { void* r = c.p + c.off; c.off += bytes; total_used_ += bytes; return r; }
+  for (size_t i = cur_; i < chunks_.size(); ++i) {
+    Chunk& c = chunks_[i];
+    if (i > cur_ && c.off != 0) break;                 // chunks past the current one are empty by construction
+    if (c.off + bytes <= c.cap) {
+      void* r = c.p + c.off;
+      // bytes skipped at the end of the chunks in between count as used: release_to() gives them back with the chunk
+      for (size_t j = cur_; j < i; ++j) { total_used_ += chunks_[j].cap - chunks_[j].off; chunks_[j].off = chunks_[j].cap; }
+      c.off += bytes; total_used_ += bytes; cur_ = i;
+      if (total_used_ > peak_) peak_ = total_used_;
+      return r;
+    }
   }
   size_t cap = std::max(bytes, size_t(256) << 20);
   char* p = nullptr;
   if (cudaMalloc(&p, cap) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  for (size_t j = cur_; j < chunks_.size(); ++j) { total_used_ += chunks_[j].cap - chunks_[j].off; chunks_[j].off = chunks_[j].cap; }
   chunks_.push_back({p, cap, bytes});
+  cur_ = chunks_.size() - 1;
   total_used_ += bytes;
+  if (total_used_ > peak_) peak_ = total_used_;
   return p;
+}
+void Arena::release_to(const Mark& m) {
+  if (chunks_.empty() || m.chunk >= chunks_.size()) return;
+  for (size_t i = m.chunk + 1; i < chunks_.size(); ++i) { total_used_ -= chunks_[i].off; chunks_[i].off = 0; }
+  total_used_ -= chunks_[m.chunk].off - m.off;
+  chunks_[m.chunk].off = m.off;
+  cur_ = m.chunk;
 }
 
 // ======================================================================================================
@@ -389,6 +414,14 @@ struct Run {
     if (!p) set_error("workspace allocation of %zu bytes failed", n * sizeof(T));
     return p;
   }
+  // workspace scopes (Arena): everything allocated since `m` is handed back; the launches that use it are already queued on
+  // the engine's one stream, ahead of whatever reuses the memory.  The operand-image scratch may live in the released region.
+  Arena::Mark mark() const { return e.arena.mark(); }
+  void release_to(const Arena::Mark& m) {
+    if (xpack && (m.chunk < xpack_at.chunk || (m.chunk == xpack_at.chunk && m.off <= xpack_at.off))) { xpack = nullptr; xpack_bytes = 0; }
+    e.arena.release_to(m);
+  }
+  Arena::Mark xpack_at{0, 0};
   // ---- segment tables: reserve device space first, fill host staging, upload once -----------------
   int tables_begin(size_t cap) {
     d_tables = (char*)e.arena.alloc(cap);
@@ -505,6 +538,8 @@ struct ConvCall {
   double* ostats = nullptr;
   bool tensor = false;           // eligible for the tcgen05 path (16-bit operands) when the engine runs in a tensor precision
   bool exact = false;            // text side: tcgen05 with split-fp16 operands (fp32-equivalent) in tensor precisions, FFMA in FP32
+  bool wa = false;               // 128-channel layer on the weights-as-A kernel (conv_umma_wa.cu); the table has 256-row tiles
+  bool x_f16 = false, y_f16 = false;   // wa only: x / y are fp16 rows (the c1 -> c2 intermediate of a resblock)
 };
 
 // Which kernel a convolution runs on, by precision mode:
@@ -532,6 +567,17 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   a.out_scale = c.out_scale; a.accumulate = c.accumulate; a.act = c.act; a.act_slope = c.act_slope;
   a.ostats = c.ostats; a.ld_ostats = c.w->Cout;
   a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
+  if (c.wa) {
+    // the caller sized its buffers for this kernel (fp16 intermediate, 256-row tiles): no other kernel can take the call
+    a.tile_rows = CONV_WA_TILE_ROWS; a.x_f16 = c.x_f16; a.y_f16 = c.y_f16;
+    if (!half16 || !conv_umma_wa_supported(a)) { set_error("internal: weights-as-A conv kernel refused Cin=%d Cout=%d k=%d dil=%d", a.Cin, a.Cout, a.k, a.dil); return TTSB_E_INVALID; }
+    const double rows_wa = (double)t.out_rows;
+    r.e.prof.begin(r.s, PROF_CONV_TENSOR, 2.0 * rows_wa * a.Cin * a.Cout * a.k,
+                   rows_wa * a.Cout * ((a.y_f16 ? 2.0 : 4.0) + (a.res ? 4.0 : 0.0) + (a.accumulate ? 4.0 : 0.0)) + (a.x_f16 ? 2.0 : 4.0) * (double)t.in_rows * a.Cin);
+    CK(launch_conv_umma_wa(a, r.s));
+    r.e.prof.end(r.s);
+    return TTSB_OK;
+  }
   if ((split || half16) && a.stride == 1) {
     // layers with several Cout tiles read pre-packed operand images (conv_umma.cu: pack_act_kernel); scratch sized for this call
     const int ks = split ? 64 : (a.cin_pad < 128 ? a.cin_pad : 128);
@@ -543,8 +589,9 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
       const size_t need = (size_t)t.ntiles * (a.cin_pad / ks) * slab;
       if (need > r.xpack_bytes && need <= ((size_t)512 << 20)) {
         const size_t cap = need > ((size_t)32 << 20) ? need : ((size_t)32 << 20);
+        const Arena::Mark at = r.mark();
         uint8_t* pnew = r.alloc<uint8_t>(cap);
-        if (pnew) { r.xpack = pnew; r.xpack_bytes = cap; }
+        if (pnew) { r.xpack = pnew; r.xpack_bytes = cap; r.xpack_at = at; }
       }
       a.xpack = r.xpack; a.xpack_bytes = r.xpack_bytes;
     }
@@ -638,25 +685,30 @@ int run_resblk1d(Run& r, const ResBlk1dW& b, const float* x, int ldx, const doub
 // kokoro AdaINResBlock1.  x (ld C) with statistics xstats; the running value lives in `cur` (ld C; may equal x when
 // the caller allows in-place).  The last of the three iterations writes `(x + xt) * final_scale` into `out` (accumulating if asked).
 int run_resblock1(Run& r, const ResBlock1W& b, const float* x, const double* xstats, float* cur, float* xt, float* out, float final_scale,
-                  int accumulate, double* out_stats, const float* gb, int ld_gb, const SegTab& t) {
+                  int accumulate, double* out_stats, const float* gb, int ld_gb, const SegTab& t, const SegTab* twa = nullptr) {
   const int C = b.C, nseg = t.nseg;
   const float* in = x;
   const double* in_st = xstats;
+  // twa: the 256-row tile table of the weights-as-A kernel; `xt` then holds fp16 rows (it is only ever read as a 16-bit operand)
+  const bool wa = twa != nullptr;
+  const SegTab& tt = wa ? *twa : t;
   for (int m = 0; m < 3; ++m) {
     double* st_t = r.stats(nseg, C);
     if (!st_t) return TTSB_E_NOMEM;
     ConvCall c1; c1.w = &b.c1[m]; c1.x = in; c1.ldx = C; c1.y = xt; c1.ldy = C; c1.dil = b.dil[m]; c1.pad = (b.k * b.dil[m] - b.dil[m]) / 2;
     c1.pro = PRO_ADAIN_SNAKE; c1.pstats = in_st; c1.gb = gb; c1.ld_gb = ld_gb; c1.ad = b.a1[m]; c1.alpha = b.alpha1[m]; c1.ostats = st_t; c1.tensor = true;
-    RC(run_conv(r, c1, t));
+    c1.wa = wa; c1.y_f16 = wa;
+    RC(run_conv(r, c1, tt));
     const bool last = m == 2;
     double* st_n = last ? out_stats : r.stats(nseg, C);
     if (!last && !st_n) return TTSB_E_NOMEM;
     ConvCall c2; c2.w = &b.c2[m]; c2.x = xt; c2.ldx = C; c2.dil = 1; c2.pad = (b.k - 1) / 2;
     c2.pro = PRO_ADAIN_SNAKE; c2.pstats = st_t; c2.gb = gb; c2.ld_gb = ld_gb; c2.ad = b.a2[m]; c2.alpha = b.alpha2[m];
     c2.res = in; c2.ldr = C; c2.tensor = true;
+    c2.wa = wa; c2.x_f16 = wa;
     if (last) { c2.y = out; c2.ldy = C; c2.out_scale = final_scale; c2.accumulate = accumulate; c2.ostats = out_stats; }
     else { c2.y = cur; c2.ldy = C; c2.ostats = st_n; }
-    RC(run_conv(r, c2, t));
+    RC(run_conv(r, c2, tt));
     in = cur; in_st = st_n;
   }
   return TTSB_OK;
@@ -697,6 +749,10 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   const SegTab tS0_U1 = r.make_tab(spS0, spU1);        // ups[1] polyphase
   const SegTab tU1_S1 = r.make_tab(spU1, spS1, 6, 1, false);
   const SegTab tS1 = r.make_tab(spS1, spS1);
+  // stage 1 (128 channels) in the 16-bit operand modes: the weights-as-A kernel, 256-row tiles, fp16 c1 -> c2 intermediate
+  static const bool no_wa = getenv("TTSB_NO_WA") != nullptr;
+  const bool wa1 = !no_wa && (e.precision == TTSB_PRECISION_FP16 || e.precision == TTSB_PRECISION_BF16);
+  const SegTab tS1w = wa1 ? r.make_tab(spS1, spS1, 1, 1, true, CONV_WA_TILE_ROWS) : SegTab();
   const SegTab tS1_A = r.make_tab(spS1, spA, 1, 1, false);
   // per-utterance seeds of the in-kernel SineGen noise (null: vocoder-only entry, noise keyed by position in the buffer)
   const unsigned long long* seg_seeds = (utt_seeds && (int)utt_seeds->size() == nseg) ? r.push(*utt_seeds) : nullptr;
@@ -723,21 +779,27 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
     const Space& spU = i == 0 ? spU0 : spU1;
     const SegTab& tS = i == 0 ? tS0 : tS1;
     const size_t n = (size_t)spS.total * C;
-    // x_source = noise_res[i](noise_convs[i](har))
-    float* xs = r.alloc<float>(n);
-    float* xt = r.alloc<float>(n);
-    float* xs2 = r.alloc<float>(n);
+    const size_t nup = (size_t)spU.total * s_up * C;           // the flat polyphase buffer of ups[i]: a few rows more than n
+    // Four stage-size buffers serve the whole stage (liveness: xs dies with noise_res, xs2 and up die with the upsample-add):
+    //   b0: xs -> up -> acc (the stage's output, kept)    b1: xt (fp16 rows on the weights-as-A path)    b2: xs2 -> cur    b3: x0
+    float* b0 = r.alloc<float>(std::max(n, nup));
+    const Arena::Mark stage_scope = r.mark();                   // b1..b3 (and any operand-image scratch) go back at the end of the stage
+    const SegTab* twa = (i == 1 && wa1) ? &tS1w : nullptr;
+    float* b1 = twa ? reinterpret_cast<float*>(r.alloc<__half>(n)) : r.alloc<float>(n);
+    float* b2 = r.alloc<float>(n);
+    float* b3 = r.alloc<float>(n);
     double* st_xs = r.stats(nseg, C);
-    if (!xs || !xt || !xs2 || !st_xs) return TTSB_E_NOMEM;
+    if (!b0 || !b1 || !b2 || !b3 || !st_xs) return TTSB_E_NOMEM;
+    // x_source = noise_res[i](noise_convs[i](har))
+    float *xs = b0, *xt = b1, *xs2 = b2;
     ConvCall cn; cn.x = har; cn.y = xs; cn.ldy = C; cn.ostats = st_xs; cn.tensor = true;
     if (i == 0) { cn.w = &e.noise_conv0r; cn.ldx = 144; cn.pad = 1; RC(run_conv(r, cn, tHb_S0)); }
     else { cn.w = &e.noise_conv[1]; cn.ldx = 24; RC(run_conv(r, cn, tH_S1)); }
-    RC(run_resblock1(r, e.noise_res[i], xs, st_xs, xs, xt, xs2, 1.0f, 0, nullptr, gbD, ld_gb, tS));
+    RC(run_resblock1(r, e.noise_res[i], xs, st_xs, xs, xt, xs2, 1.0f, 0, nullptr, gbD, ld_gb, tS, twa));
     // x = ups[i](leaky_relu(x, 0.1))  (+ ReflectionPad1d((1,0)) for the last stage) + x_source
-    float* up = r.alloc<float>((size_t)spU.total * s_up * C);
-    float* x0 = r.alloc<float>(n);
+    float *up = b0, *x0 = b3;
     double* st_x0 = r.stats(nseg, C);
-    if (!up || !x0 || !st_x0) return TTSB_E_NOMEM;
+    if (!st_x0) return TTSB_E_NOMEM;
     ConvCall cu; cu.w = &e.ups[i]; cu.x = xin; cu.ldx = e.ups[i].Cin; cu.y = up; cu.ldy = s_up * C; cu.pad = 1; cu.pro = PRO_LRELU; cu.slope = 0.1f; cu.tensor = true;
     RC(run_conv(r, cu, i == 0 ? tL_U0 : tS0_U1));
     const SegTab& tUS = i == 0 ? tU0_S0 : tU1_S1;
@@ -745,11 +807,10 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
     CK(launch_up_add(up, C, s_up / 2, i == 1, xs2, C, x0, C, C, tUS.segs, nseg, tUS.max_out, st_x0, C, r.s));
     e.prof.end(r.s);
     // mean of the three parallel AdaINResBlock1
-    float* acc = r.alloc<float>(n);
-    float* cur = r.alloc<float>(n);
-    if (!acc || !cur) return TTSB_E_NOMEM;
+    float *acc = b0, *cur = b2;
     for (int j = 0; j < 3; ++j)
-      RC(run_resblock1(r, e.resblk[3 * i + j], x0, st_x0, cur, xt, acc, 1.0f / 3.0f, j > 0, nullptr, gbD, ld_gb, tS));
+      RC(run_resblock1(r, e.resblk[3 * i + j], x0, st_x0, cur, xt, acc, 1.0f / 3.0f, j > 0, nullptr, gbD, ld_gb, tS, twa));
+    r.release_to(stage_scope);
     RC(r.tap(i == 0 ? "gen_stage0" : "gen_stage1", acc, spS.total, C, C));
     xin = acc;
     stage_out = acc;
@@ -1077,6 +1138,18 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
     }
   }
 
+  // what the generator still needs when the predictor / decoder intermediates are gone: allocated first, the rest is scoped
+  float* F0 = r.alloc<float>(RL);
+  float* NN = r.alloc<float>(RL);
+  float* GIN = r.alloc<float>((size_t)RL * 512);
+  float* gbD = nullptr;
+  RC(run_style(r, e.style_dec, e.d_refs, 256, B, &gbD));
+  const int ldD = e.style_dec.ldw;
+  float* d_audio = audio;
+  if (audio_mem != TTSB_MEM_DEVICE) d_audio = r.alloc<float>((size_t)RF * 600);
+  if (!F0 || !NN || !GIN || !d_audio) return TTSB_E_NOMEM;
+  const Arena::Mark front_scope = r.mark();
+
   // ---- alignment index map + length regulation (A.5) ----
   int* d_idx = r.alloc<int>(RF);
   float* EN = r.alloc<float>((size_t)RF * 640);
@@ -1099,9 +1172,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   float* GX = r.alloc<float>((size_t)RF * 2048);
   float* SH = r.alloc<float>((size_t)RF * 512);
   double* st_sh = r.stats(B, 512);
-  float* F0 = r.alloc<float>(RL);
-  float* NN = r.alloc<float>(RL);
-  if (!GX || !SH || !st_sh || !F0 || !NN) return TTSB_E_NOMEM;
+  if (!GX || !SH || !st_sh) return TTSB_E_NOMEM;
   RC(run_bilstm(r, e.shared_lstm, EN, 640, GX, SH, 512, tF, d_lsF, (int)g_lsF.size(), false));
   CK(launch_colstats(SH, 512, 512, tF.segs, B, spF.maxlen, st_sh, 512, r.s));
   for (int br = 0; br < 2; ++br) {
@@ -1129,17 +1200,13 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   RC(r.tap("N", NN, RL, 1, 1));
 
   // ---- decoder (A.10) ----
-  float* gbD = nullptr;
-  RC(run_style(r, e.style_dec, e.d_refs, 256, B, &gbD));
-  const int ldD = e.style_dec.ldw;
   CK(launch_conv1_s2(F0, CAT0 + 512, 516, e.f0conv_w, e.f0conv_b, tLF.segs, B, spF.maxlen, nullptr, 0, r.s));
   CK(launch_conv1_s2(NN, CAT0 + 513, 516, e.nconv_w, e.nconv_b, tLF.segs, B, spF.maxlen, nullptr, 0, r.s));
   double* st_cat0 = r.stats(B, 514);
   float* XDa = r.alloc<float>((size_t)RF * 1092);
   float* XDb = r.alloc<float>((size_t)RF * 1092);
   double* st_a = r.stats(B, 1090); double* st_b = r.stats(B, 1090);
-  float* GIN = r.alloc<float>((size_t)RL * 512);
-  if (!st_cat0 || !XDa || !XDb || !st_a || !st_b || !GIN) return TTSB_E_NOMEM;
+  if (!st_cat0 || !XDa || !XDb || !st_a || !st_b) return TTSB_E_NOMEM;
   CK(launch_colstats(CAT0, 516, 514, tF.segs, B, spF.maxlen, st_cat0, 514, r.s));
   CK(cudaMemsetAsync(XDa, 0, sizeof(float) * (size_t)RF * 1092, r.s));
   CK(cudaMemsetAsync(XDb, 0, sizeof(float) * (size_t)RF * 1092, r.s));
@@ -1173,11 +1240,7 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   RC(r.tap("gen_in", GIN, RL, 512, 512));
 
   // ---- generator (A.11) ----
-  float* d_audio = audio;
-  if (audio_mem != TTSB_MEM_DEVICE) {
-    d_audio = r.alloc<float>((size_t)RF * 600);
-    if (!d_audio) return TTSB_E_NOMEM;
-  }
+  r.release_to(front_scope);             // EN, CAT0, the LSTM gates, the F0/N and decoder intermediates: their launches are queued
   // the noise an utterance draws depends on (seed, its own token ids), not on where it sits in the batch or on its neighbours
   std::vector<unsigned long long> utt_seeds(e.utt_key.size());
   for (size_t b = 0; b < utt_seeds.size(); ++b) {

@@ -97,17 +97,25 @@ struct Profiler {
   void release() { for (auto ev : events) cudaEventDestroy(ev); events.clear(); }
 };
 
+// Workspace of one engine: a stack allocator over a few large device allocations.  Everything of a step runs on ONE stream, so a
+// buffer may be handed out again as soon as the launches that use it are QUEUED: release_to(mark) pops everything allocated since
+// mark() (stream order keeps the earlier kernels ahead of the later writers).  Scopes nest; the peak is what a step really needs.
 class Arena {
  public:
+  struct Mark { size_t chunk, off; };
   ~Arena() { release(); }
   void release();
   void reset();                           // start a new synthesis (may consolidate chunks)
   void* alloc(size_t bytes);              // 256-byte aligned; nullptr on failure
+  Mark mark() const { return {cur_, chunks_.empty() ? 0 : chunks_[cur_].off}; }
+  void release_to(const Mark& m);
   size_t used() const { return total_used_; }
+  size_t peak() const { return peak_; }   // high-water mark since the last reset()
  private:
   struct Chunk { char* p; size_t cap, off; };
   std::vector<Chunk> chunks_;
-  size_t total_used_ = 0;
+  size_t cur_ = 0;                        // chunk the next allocation is tried in first
+  size_t total_used_ = 0, peak_ = 0;
 };
 
 struct Engine {

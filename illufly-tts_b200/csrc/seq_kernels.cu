@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_kernel(const float* __restri
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         const float* __restrict__ gb, int ld_gb, const int* __restrict__ row2seg,
                                                         int act, float slope) {
+  pdl_trigger();
+  pdl_wait();               // before any return: every CTA waits for the previous kernel (common.cuh, programmatic dependent launch)
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -162,6 +164,8 @@ __global__ void __launch_bounds__(256) attention_kernel(const float* __restrict_
   float (*kv)[ATT_LD] = reinterpret_cast<float (*)[ATT_LD]>(att_smem);                  // [ATT_KC][ATT_LD]
   float (*qs)[64] = reinterpret_cast<float (*)[64]>(att_smem + ATT_KC * ATT_LD);       // [ATT_QB][64]
   float* S = att_smem + ATT_KC * ATT_LD + ATT_QB * 64;                                  // [ATT_QB][ld_s]
+  pdl_trigger();
+  pdl_wait();               // before any return: every CTA waits for the previous kernel (common.cuh, programmatic dependent launch)
   const Seg seg = segs[blockIdx.z];
   const int head = blockIdx.y;
   const int q0 = blockIdx.x * ATT_QB;
@@ -365,7 +369,9 @@ cudaError_t launch_layernorm(const float* x, int ldx, const float* res, int ldr,
                              int act, float slope, cudaStream_t s) {
   if (rows <= 0) return cudaSuccess;
   if (C > 32 * MAXV) return cudaErrorInvalidValue;
-  layernorm_kernel<<<(rows + 7) / 8, 256, 0, s>>>(x, ldx, res, ldr, out, ldo, rows, C, eps, mode, gamma, beta, gb, ld_gb, row2seg, act, slope);
+  cudaError_t le = launch_pdl(layernorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, x, ldx, res, ldr, out, ldo, rows, C, eps, mode, gamma, beta, gb, ld_gb, row2seg,
+                              act, slope);
+  if (le != cudaSuccess) return le;
   return launched();
 }
 cudaError_t launch_albert_embed(const int* ids, const int* pos, const float* word, const float* posw, const float* type0,
@@ -400,7 +406,8 @@ cudaError_t launch_attention(const float* qkv, float* ctx, const Seg* segs, int 
     attr_set[dev] = true;
   }
   dim3 grid((max_len + ATT_QB - 1) / ATT_QB, heads, nseg);
-  attention_kernel<<<grid, 256, smem, s>>>(qkv, ctx, segs, heads, ld_s);
+  cudaError_t le = launch_pdl(attention_kernel, grid, dim3(256), smem, s, qkv, ctx, segs, heads, ld_s);
+  if (le != cudaSuccess) return le;
   return launched();
 }
 cudaError_t launch_duration(const float* logits, int ld, int nbins, const int* row2seg, const float* speeds, float* duration, int* pred_dur,

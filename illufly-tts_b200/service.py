@@ -30,12 +30,15 @@ is one phoneme string), wav files, HTTP.  There is no CPU fallback: the model is
 from __future__ import annotations
 
 import asyncio
+import logging
 import time
 import uuid
 from enum import Enum
 from typing import Any, AsyncGenerator, Callable, Dict, List, Mapping, Optional, Sequence
 
 import torch
+
+logger = logging.getLogger(__name__)
 
 
 class TaskStatus(Enum):                       # service.py:22-27
@@ -87,6 +90,17 @@ class TTSServiceManager:
         :53, and never reads it)."""
         if token_budget <= 0 or max_batch_items <= 0:
             raise ValueError("token_budget and max_batch_items must be positive")
+        # A BatchKModel in the reference's compatibility mode (strict=False) swallows engine failures and returns a second of silence
+        # per item: the failed requests would be COMPLETED with silence and the bisection below would never run.  The service needs
+        # failures to raise, so it switches the model to strict; and it warns when the model batches with the reference's padded
+        # duration LSTM, where a request's durations depend on the longest request it happens to share a batch with.
+        if hasattr(model, "strict") and not model.strict:
+            logger.warning("TTSServiceManager: switching the model to strict=True (engine failures must raise to be isolated)")
+            model.strict = True
+        if getattr(model, "padded_lstm", False):
+            logger.warning("TTSServiceManager: the model runs with padded_lstm=True: a request's durations depend on its batch; "
+                           "construct BatchKModel(..., padded_lstm=False) for batch-invariant results")
+        self.task_ttl = 3600.0                             # finished tasks are forgotten after this many seconds (evict_finished)
         self.model = model
         self.voices = voices
         self.token_budget = token_budget
@@ -219,6 +233,16 @@ class TTSServiceManager:
                 break
         return batch
 
+    def evict_finished(self, now: Optional[float] = None) -> int:
+        """forget COMPLETED / FAILED / CANCELED tasks older than ``task_ttl`` (the reference keeps every task for ever); called
+        once per batch round, so ``tasks`` - which select_batch scans - stays proportional to the live load"""
+        now = time.time() if now is None else now
+        dead = [k for k, t in self.tasks.items()
+                if t.status not in (TaskStatus.PENDING, TaskStatus.PROCESSING) and now - (t.completed_at or t.created_at) > self.task_ttl]
+        for k in dead:
+            del self.tasks[k]
+        return len(dead)
+
     def _run(self, units: List[tuple]) -> List[torch.Tensor]:
         """One engine call for ``units`` = [(phonemes, style row [1,256], speed)].  Worker thread."""
         ph = [u[0] for u in units]
@@ -244,6 +268,7 @@ class TTSServiceManager:
     async def _batch_processing_loop(self) -> None:
         assert self._wake is not None
         while True:
+            self.evict_finished()
             batch = self.select_batch()
             if not batch:
                 self._wake.clear()

@@ -215,7 +215,7 @@ class DurationEncoder(nn.Module):
                 packed = nn.utils.rnn.pack_padded_sequence(x, text_lengths.cpu(), batch_first=True, enforce_sorted=False)
                 y, _ = block(packed)
                 y, _ = nn.utils.rnn.pad_packed_sequence(y, batch_first=True)
-                x = torch.zeros(y.shape[0], Tm, y.shape[2])
+                x = torch.zeros(y.shape[0], Tm, y.shape[2], device=y.device)
                 x[:, : y.shape[1]] = y
         return x  # [B,T,640]
 
@@ -327,7 +327,7 @@ class TextEncoder(nn.Module):
         packed = nn.utils.rnn.pack_padded_sequence(x, lengths.cpu(), batch_first=True, enforce_sorted=False)
         y, _ = self.lstm(packed)
         y, _ = nn.utils.rnn.pad_packed_sequence(y, batch_first=True)
-        out = torch.zeros(y.shape[0], m.shape[-1], y.shape[2])
+        out = torch.zeros(y.shape[0], m.shape[-1], y.shape[2], device=y.device)
         out[:, : y.shape[1]] = y
         return out.transpose(1, 2).masked_fill(mm, 0.0)  # [B,512,T]
 
@@ -367,7 +367,7 @@ def harmonic_phase(f0: torch.Tensor, upsample_scale: int, sr: int, harmonics: in
     """SineGen._f02sine up to (not including) sin(): f0 [B,L] -> phase [B, L*scale, H] (fp32).
     rand_ini omitted (no effect)."""
     f0u = F.interpolate(f0[:, None, :], scale_factor=float(upsample_scale), mode="nearest").transpose(1, 2)  # [B,N,1]
-    fn = f0u * torch.arange(1, harmonics + 1, dtype=torch.float32)[None, None, :]
+    fn = f0u * torch.arange(1, harmonics + 1, dtype=torch.float32, device=f0.device)[None, None, :]
     rad = (fn / sr) % 1
     rad = F.interpolate(rad.transpose(1, 2), scale_factor=1 / upsample_scale, mode="linear").transpose(1, 2)
     phase = torch.cumsum(rad, dim=1) * 2 * torch.pi
@@ -544,7 +544,7 @@ class KokoroOracle(nn.Module):
     def front(self, padded_ids, input_lengths, ref_s, speeds):
         """Batched front half, kmodel.py:62-103 (incl. the un-packed predictor.lstm, App. C-1)."""
         B, Tm = padded_ids.shape
-        text_mask = torch.arange(Tm)[None].expand(B, -1) + 1 > input_lengths[:, None]
+        text_mask = torch.arange(Tm, device=padded_ids.device)[None].expand(B, -1) + 1 > input_lengths[:, None]
         bert_dur = self.bert(padded_ids, attention_mask=(~text_mask).int())
         d_en = self.bert_encoder(bert_dur).transpose(-1, -2)
         style = ref_s[:, 128:]
@@ -566,36 +566,38 @@ class KokoroOracle(nn.Module):
         speeds = speeds or [1.0] * B
         if ref_s.dim() == 3:
             ref_s = ref_s.squeeze(1)
-        lengths = torch.tensor([len(x) for x in ids_list], dtype=torch.long)
+        dev = self.bert_encoder.weight.device       # cpu, or a GPU for bench.py's eager-PyTorch baseline (same graph, stock kernels)
+        ref_s = ref_s.to(dev)
+        lengths = torch.tensor([len(x) for x in ids_list], dtype=torch.long, device=dev)
         Tm = int(lengths.max())
-        padded = torch.zeros(B, Tm, dtype=torch.long)
+        padded = torch.zeros(B, Tm, dtype=torch.long, device=dev)
         for i, ids in enumerate(ids_list):
-            padded[i, : len(ids)] = torch.tensor(ids, dtype=torch.long)
+            padded[i, : len(ids)] = torch.tensor(ids, dtype=torch.long, device=dev)
         d, duration, text_mask = self.front(padded, lengths, ref_s, speeds)
         out = OracleOutput([], [], [], [])
         for i in range(B):  # kmodel.py:108-144
             L = int(lengths[i])
             cur = duration[i, :L]
             pred_dur = torch.round(cur).clamp(min=1).long()
-            indices = torch.repeat_interleave(torch.arange(L), pred_dur)
+            indices = torch.repeat_interleave(torch.arange(L, device=dev), pred_dur)
             out.duration.append(cur.clone())
             out.pred_dur.append(pred_dur)
             out.indices.append(indices)
             if stop_after_durations:
                 continue
             Fr = int(indices.shape[0])
-            aln = torch.zeros(L, Fr)
-            aln[indices, torch.arange(Fr)] = 1
+            aln = torch.zeros(L, Fr, device=dev)
+            aln[indices, torch.arange(Fr, device=dev)] = 1
             aln = aln[None]
             s_i = ref_s[i: i + 1, 128:]
             en = d[i: i + 1, :L].transpose(-1, -2) @ aln
             F0, N = self.predictor.F0Ntrain(en, s_i)
-            t_en = self.text_encoder(padded[i: i + 1, :L], torch.tensor([L]), text_mask[i: i + 1, :L])
+            t_en = self.text_encoder(padded[i: i + 1, :L], torch.tensor([L]), text_mask[i: i + 1, :L])     # lengths stay on the CPU (packing)
             asr = t_en @ aln
             if noise is not None:
-                nz = noise[i]
+                nz = noise[i].to(dev)
             else:
-                nz = make_noise(noise_seed, i, Fr)
+                nz = make_noise(noise_seed, i, Fr).to(dev)
             taps = {} if want_taps else None
             audio = self.decoder(asr, F0, N, ref_s[i: i + 1, :128], nz[None], taps).squeeze()
             if want_taps:

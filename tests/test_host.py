@@ -135,6 +135,43 @@ dist.destroy_process_group()
     assert d["tmax"] == 2.0 and d["n"] == 64 and d["tokens"] == d["want"]
 
 
+def test_bench_fleet_partition_world_size_2_gloo(tmp_path):
+    """bench.py --workload fleet (BASELINE configs[4]): every rank builds the SAME fleet, takes its LPT share and cuts it into
+    token-budgeted micro-batches; over two gloo ranks every utterance is synthesised exactly once, no micro-batch exceeds the budget,
+    and the predicted work of the two shares differs by less than one utterance"""
+    script = tmp_path / "f.py"
+    script.write_text(f'''
+import os, sys, json, importlib.util
+sys.path.insert(0, {ROOT!r})
+import torch, torch.distributed as dist
+spec = importlib.util.spec_from_file_location("bench_mod", os.path.join({ROOT!r}, "bench.py"))
+bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+w, mine, mbs, my_cost, all_cost = bench.make_fleet(256, rank, world, 1200)
+seen = torch.zeros(256, dtype=torch.int32)
+for mb in mbs:
+    assert sum(len(w["ids"][i]) for i in mb) <= 1200 or len(mb) == 1
+    for i in mb:
+        seen[i] += 1
+dist.all_reduce(seen)
+cost = torch.tensor([my_cost], dtype=torch.float64)
+lo, hi = cost.clone(), cost.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+if rank == 0:
+    longest = max(len(x) / s for x, s in zip(w["ids"], w["speeds"]))
+    print(json.dumps(dict(once=bool((seen == 1).all()), spread=hi.item() - lo.item(), longest=longest, nmb=len(mbs))))
+dist.barrier()
+dist.destroy_process_group()
+''')
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29617",
+                        str(script)], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["once"] and d["spread"] <= d["longest"] and d["nmb"] >= 5
+
+
 def test_bench_reference_arm_runs_on_cpu():
     """--impl reference is the CPU oracle arm: must print one JSON line without a GPU"""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-utts", "1"],

@@ -285,3 +285,31 @@ def test_a_task_that_cannot_be_assembled_fails_alone_and_the_loop_survives():
         assert svc.tasks[later].status == pkg.TaskStatus.COMPLETED and not svc.processing_task.done()
         await svc.stop()
     run(main())
+
+
+def test_service_forces_strict_and_evicts_finished_tasks():
+    """a model in the reference's compatibility mode (failures -> silence) would make failed requests COMPLETED with silence: the
+    service switches it to strict; finished tasks are forgotten after task_ttl"""
+    import asyncio
+
+    class Compat:
+        strict = False
+        padded_lstm = False
+
+        def forward_batch(self, ph, ref, speeds=None):
+            return [torch.zeros(600 * len(p)) for p in ph]
+    m = Compat()
+    svc = pkg.TTSServiceManager(m, {"v": torch.zeros(510, 1, 256)})
+    assert m.strict is True
+
+    async def main():
+        tid = await svc.submit_task("abcdefgh", "v")
+        await svc.start()
+        async for _ in svc.stream_result(tid):
+            pass
+        await svc.stop()
+        return tid
+    tid = asyncio.run(main())
+    assert svc.tasks[tid].status == pkg.TaskStatus.COMPLETED
+    assert svc.evict_finished(now=svc.tasks[tid].completed_at + 10) == 0 and tid in svc.tasks
+    assert svc.evict_finished(now=svc.tasks[tid].completed_at + svc.task_ttl + 1) == 1 and tid not in svc.tasks
