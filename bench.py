@@ -511,6 +511,8 @@ def main():
                              # the same region with the engine's pinned staging buffer: ONE D2H copy of the batch.  Not the default of the drop-in class
                              # because its result would alias an engine-owned buffer, and the reference's callers keep what they get (pipeline.py:829)
                              value_pinned_host_buffer=audio_total * e2e_steps / e2e_pin_max),
+                    workspace=dict(peak_bytes=eng.workspace_peak_bytes(), per_frame_bytes=eng.workspace_peak_bytes() / max(sum(frames[-len(batches[-1]["ids"]):]), 1),
+                                   note="high-water mark of the engine's stack-allocated workspace in the last step (last micro-batch for the fleet)"),
                     gpu_launches=int(launches_total), clocks=clk, roofline=roofline, hbm_kernels=hbm,
                     profile_ms_per_step={k: v["ms"] / args.steps for k, v in prof_acc.items()},
                     # share of the device-timed step covered by the event-timed categories (the rest: small kernels, host gap between the halves)

@@ -29,6 +29,7 @@ SIGNATURES = {
     "ttsb_engine_enable_taps": (C.c_int, [_p, C.c_int]),
     "ttsb_engine_launch_count": (C.c_int64, [_p]),
     "ttsb_engine_last_step_ms": (C.c_int, [_p, _f32p]),
+    "ttsb_engine_workspace_peak": (C.c_int, [_p, _i64p]),
     "ttsb_engine_profile": (C.c_int, [_p, C.c_int]),
     "ttsb_engine_profile_read": (C.c_int, [_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _i64p]),
     "ttsb_synthesize_begin": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p]),

@@ -575,12 +575,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       const bool tile_fast = tile.t0 + BM <= seg.out_len && p.act == ACT_NONE && !(u.dbg & 2);
       const size_t row0 = (size_t)(seg.out_off + tile.t0 + q * 32 + (lane >> 3));
       const size_t ystep = (size_t)4 * p.ldy, rstep = (size_t)4 * p.ldr;
+      // bias of the chunk: requested one chunk ahead (the first before the wait for the accumulator).  Loaded at its point of use it
+      // cost a full L2 round trip per chunk: ncu put 23 % of the epilogue warps' stall samples on the first FFMA that reads it.
+      float4 b4n = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias && n0 + cc + 3 < p.Cout) b4n = *reinterpret_cast<const float4*>(p.bias + n0 + cc);
       mbar_wait_t(bar_acc_full(slot), (n >> 1) & 1u, tw_full);
       tc_fence_after();
       const uint32_t tacc = tmem_base + slot * (uint32_t)pl.acc_cols + ((uint32_t)(q * 32) << 16);
       for (int chunk = 0; chunk < nchunk; ++chunk) {
         const int c0 = chunk * 32;
         const int co = n0 + c0 + cc;
+        const float4 b4c = b4n;
+        b4n = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && chunk + 1 < nchunk && co + 32 + 3 < p.Cout) b4n = *reinterpret_cast<const float4*>(p.bias + co + 32);
         // residual rows of this chunk: requested before the TMEM load and the staging writes below (they do not depend on them)
         float4 r4[8];
         const bool chunk_fast = tile_fast && co + 3 < p.Cout;
@@ -613,8 +620,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         const bool colok = co < p.Cout && !(u.dbg & 2);
         const bool full4 = co + 3 < p.Cout;
         if (colok && full4 && tile_fast) {
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + co);
+          const float4 b4 = b4c;
           float* yb = p.y + row0 * p.ldy + co;
           const bool sc = p.out_scale != 1.0f;
           if (p.res && p.accumulate) epi_chunk_fast<true, true, true>(stg, lane, acs, p.out_scale, b4, yb, ystep, r4, ps, pq);
@@ -626,8 +632,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         } else if (colok && full4) {
           // all global reads of the chunk first (res / y may alias the output, so the compiler cannot hoist them itself)
           float4 y4[8];
-          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) b4 = *reinterpret_cast<const float4*>(p.bias + co);
+          const float4 b4 = b4c;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int t = tile.t0 + q * 32 + 4 * i + (lane >> 3);
@@ -690,9 +695,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
             ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);  pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 8);
             ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16); pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 16);
           }
-          if (lane < 8) {        // one owner per (row quadrant, channel): running sums over this CTA's consecutive tiles
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { s_sum[q * 256 + c0 + cc + e] += (double)ps[e]; s_sq[q * 256 + c0 + cc + e] += (double)pq[e]; }
+          // after the butterfly every lane holds the totals of its four columns; lane l adds ONE of them (column cc + (l >> 3)):
+          // one owner per (row quadrant, channel), two FP64 adds per chunk with all lanes busy instead of eight on a quarter of
+          // the warp (ncu: 8 % of the epilogue's stall samples sat on the FP64 pipe).  Running sums over this CTA's consecutive tiles.
+          {
+            const int e = lane >> 3;
+            const float vs = e == 0 ? ps[0] : e == 1 ? ps[1] : e == 2 ? ps[2] : ps[3];
+            const float vq = e == 0 ? pq[0] : e == 1 ? pq[1] : e == 2 ? pq[2] : pq[3];
+            s_sum[q * 256 + c0 + cc + e] += (double)vs;
+            s_sq[q * 256 + c0 + cc + e] += (double)vq;
           }
         }
       }

@@ -406,7 +406,9 @@ struct Run {
   size_t tables_cap = 0;
   double* stats_base = nullptr; size_t stats_cap = 0, stats_off = 0;
   uint8_t* xpack = nullptr; size_t xpack_bytes = 0;     // scratch of the pre-packed operand images (text-side GEMMs), reused call after call
+  Run* parent = nullptr;          // a side-stream Run (independent branch of the graph) draws statistics slots from its parent's pool
   explicit Run(Engine& en) : e(en), s(en.stream) {}
+  Run(Run& par, cudaStream_t side) : e(par.e), s(side), parent(&par) {}
 
   template <typename T>
   T* alloc(size_t n) {
@@ -489,6 +491,7 @@ struct Run {
     return TTSB_OK;
   }
   double* stats(int nseg, int C) {
+    if (parent) return parent->stats(nseg, C);
     const size_t n = (size_t)nseg * C * 2;
     if (stats_off + n > stats_cap) { set_error("internal: statistics pool exhausted"); return nullptr; }
     double* p = stats_base + stats_off;
@@ -862,6 +865,7 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   if (B <= 0 || !ids || !token_offsets || !ref_s || !pred_dur || !frame_offsets) { set_error("begin: bad arguments"); return TTSB_E_INVALID; }
   CK(cudaSetDevice(e.device));
   e.begun = false;
+  CK(cudaStreamSynchronize(e.stream2));      // idle unless the previous step failed between a fork and its join: the workspace is about to be reused
   e.arena.reset();
   Run r(e);
   e.prof.reset();
@@ -1175,26 +1179,39 @@ int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, i
   if (!GX || !SH || !st_sh) return TTSB_E_NOMEM;
   RC(run_bilstm(r, e.shared_lstm, EN, 640, GX, SH, 512, tF, d_lsF, (int)g_lsF.size(), false));
   CK(launch_colstats(SH, 512, 512, tF.segs, B, spF.maxlen, st_sh, 512, r.s));
+  // The F0 and the N branch are independent (three AdainResBlk1d + a projection each, 70-80 CTAs per launch): the N branch runs on
+  // the engine's second stream, forked after the shared LSTM and joined before the decoder reads both curves.
+  static const bool one_stream = getenv("TTSB_ONE_STREAM") != nullptr;
+  Run r2(r, one_stream ? r.s : e.stream2);
+  if (!one_stream) {
+    CK(cudaEventRecord(e.ev_fork, r.s));
+    CK(cudaStreamWaitEvent(e.stream2, e.ev_fork, 0));
+  }
   for (int br = 0; br < 2; ++br) {
+    Run& rr = br == 0 ? r : r2;
     const ResBlk1dW* blk = br == 0 ? e.f0_blk : e.n_blk;
     float* o0 = r.alloc<float>((size_t)RF * 512);
     float* o1 = r.alloc<float>((size_t)RL * 256);
     float* o2 = r.alloc<float>((size_t)RL * 256);
     double* s0 = r.stats(B, 512); double* s1 = r.stats(B, 256);
     if (!o0 || !o1 || !o2 || !s0 || !s1) return TTSB_E_NOMEM;
-    RC(run_resblk1d(r, blk[0], SH, 512, st_sh, o0, 512, s0, gbP, ldP, tF, tF, tF, true));
-    RC(run_resblk1d(r, blk[1], o0, 512, s0, o1, 256, s1, gbP, ldP, tF, tL, tFL, true));
-    RC(run_resblk1d(r, blk[2], o1, 256, s1, o2, 256, nullptr, gbP, ldP, tL, tL, tL, true));
+    RC(run_resblk1d(rr, blk[0], SH, 512, st_sh, o0, 512, s0, gbP, ldP, tF, tF, tF, true));
+    RC(run_resblk1d(rr, blk[1], o0, 512, s0, o1, 256, s1, gbP, ldP, tF, tL, tFL, true));
+    RC(run_resblk1d(rr, blk[2], o1, 256, s1, o2, 256, nullptr, gbP, ldP, tL, tL, tL, true));
     const ConvW& pw = br == 0 ? e.f0_proj : e.n_proj;
     static const bool proj_simt = getenv("TTSB_ROWDOT_SIMT") != nullptr;        // the tiled fp32 conv kernel: kept for bit-for-bit checks
     if (!proj_simt && pw.k == 1 && pw.Cout == 1 && pw.Cin <= 512) {
-      r.e.prof.begin(r.s, PROF_PROJ, 2.0 * RL * pw.Cin, 4.0 * RL * (pw.Cin + 1.0));
-      CK(launch_rowdot(o2, 256, RL, pw.Cin, pw.w, pw.ldw, pw.bias, br == 0 ? F0 : NN, 1, r.s));
-      r.e.prof.end(r.s);
+      e.prof.begin(rr.s, PROF_PROJ, 2.0 * RL * pw.Cin, 4.0 * RL * (pw.Cin + 1.0));
+      CK(launch_rowdot(o2, 256, RL, pw.Cin, pw.w, pw.ldw, pw.bias, br == 0 ? F0 : NN, 1, rr.s));
+      e.prof.end(rr.s);
     } else {
       ConvCall c; c.w = &pw; c.x = o2; c.ldx = 256; c.y = br == 0 ? F0 : NN; c.ldy = 1;
-      RC(run_conv(r, c, tL));
+      RC(run_conv(rr, c, tL));
     }
+  }
+  if (!one_stream) {
+    CK(cudaEventRecord(e.ev_join, e.stream2));
+    CK(cudaStreamWaitEvent(r.s, e.ev_join, 0));
   }
   RC(r.tap("F0", F0, RL, 1, 1));
   RC(r.tap("N", NN, RL, 1, 1));

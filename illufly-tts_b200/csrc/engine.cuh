@@ -121,6 +121,8 @@ class Arena {
 struct Engine {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;               // independent branches of the graph (the N branch of F0Ntrain) run here, forked / joined by events
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr, ev_step0 = nullptr, ev_step1 = nullptr;
   Profiler prof;
   int precision = 0;

@@ -107,6 +107,9 @@ int ttsb_engine_create(int cuda_device, ttsb_engine** out) {
   h->e.device = cuda_device;
   auto setup = [&]() -> int {
     CKA(cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking));
+    CKA(cudaStreamCreateWithFlags(&h->e.stream2, cudaStreamNonBlocking));
+    CKA(cudaEventCreateWithFlags(&h->e.ev_fork, cudaEventDisableTiming));
+    CKA(cudaEventCreateWithFlags(&h->e.ev_join, cudaEventDisableTiming));
     CKA(cudaEventCreate(&h->e.ev0));
     CKA(cudaEventCreate(&h->e.ev1));
     CKA(cudaEventCreateWithFlags(&h->e.ev_sync, cudaEventDisableTiming));
@@ -127,6 +130,7 @@ int ttsb_engine_destroy(ttsb_engine* h) {
   Engine& e = h->e;
   cudaSetDevice(e.device);
   if (e.stream) cudaStreamSynchronize(e.stream);
+  if (e.stream2) cudaStreamSynchronize(e.stream2);
   for (void* p : e.dev_allocs) cudaFree(p);
   for (auto& kv : e.taps) if (kv.second.d) cudaFree(kv.second.d);
   e.arena.release();
@@ -139,6 +143,9 @@ int ttsb_engine_destroy(ttsb_engine* h) {
   if (e.ev_step0) cudaEventDestroy(e.ev_step0);
   if (e.ev_step1) cudaEventDestroy(e.ev_step1);
   e.prof.release();
+  if (e.ev_fork) cudaEventDestroy(e.ev_fork);
+  if (e.ev_join) cudaEventDestroy(e.ev_join);
+  if (e.stream2) cudaStreamDestroy(e.stream2);
   if (e.stream) cudaStreamDestroy(e.stream);
   delete h;
   return TTSB_OK;
@@ -175,6 +182,12 @@ int ttsb_engine_enable_taps(ttsb_engine* h, int on) {
   return TTSB_OK;
 }
 int64_t ttsb_engine_launch_count(ttsb_engine* h) { (void)h; return (int64_t)g_launches; }
+
+int ttsb_engine_workspace_peak(ttsb_engine* h, int64_t* bytes) {
+  if (!h || !bytes) { set_error("workspace_peak: bad arguments"); return TTSB_E_INVALID; }
+  *bytes = (int64_t)h->e.arena.peak();
+  return TTSB_OK;
+}
 
 int ttsb_engine_last_step_ms(ttsb_engine* h, float* ms) {
   if (!h || !ms) { set_error("last_step_ms: bad arguments"); return TTSB_E_INVALID; }

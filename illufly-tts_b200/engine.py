@@ -118,6 +118,12 @@ class Engine:
         _lib.check(self._lib.ttsb_engine_last_step_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def workspace_peak_bytes(self) -> int:
+        """high-water mark of the engine's workspace during the last step"""
+        n = C.c_int64(0)
+        _lib.check(self._lib.ttsb_engine_workspace_peak(self._h, C.byref(n)))
+        return int(n.value)
+
     PROFILE_CATEGORIES = ("conv_tensor", "conv_fp32", "lstm", "istft", "upsample_add", "gather", "attention", "layernorm", "harmonic_source",
                           "fp32_projections")
 

@@ -92,6 +92,11 @@ TTSB_API int ttsb_engine_enable_taps(ttsb_engine* e, int on);
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 TTSB_API int64_t ttsb_engine_launch_count(ttsb_engine* e);
 
+/* high-water mark (bytes) of the engine's workspace during the last synthesis / vocoder step.  The workspace is a stack allocator:
+ * stage buffers are handed back as soon as the launches that use them are queued (one stream), so the mark is what a batch really
+ * needs - about 0.3 MB per decoder frame in the 16-bit operand modes */
+TTSB_API int ttsb_engine_workspace_peak(ttsb_engine* e, int64_t* bytes);
+
 /* device time (ms) of the last synthesis / vocoder step: CUDA events on the engine's stream from the first launch of
  * begin() (or vocoder()) to the last operation of finish(), host gaps between the two phases included */
 TTSB_API int ttsb_engine_last_step_ms(ttsb_engine* e, float* ms);
