@@ -12,8 +12,9 @@ There is no CPU fallback: importing works anywhere, creating an engine needs the
 """
 from .engine import Engine, SynthesisResult, PRECISION_FP32, PRECISION_BF16, PRECISION_FP16, PRECISION_FP32_FFMA  # noqa: F401
 from .kmodel import BatchKModel, install_into_reference  # noqa: F401
+from .egress import wav_base64, wav_float32_bytes  # noqa: F401
 from .partition import lpt_partition, micro_batches  # noqa: F401
 from .service import ReferencePolicyManager, TaskStatus, TTSServiceManager, TTSTask  # noqa: F401
 
-__all__ = ["Engine", "SynthesisResult", "BatchKModel", "install_into_reference", "lpt_partition", "micro_batches", "TTSServiceManager", "ReferencePolicyManager", "TaskStatus", "TTSTask",
+__all__ = ["Engine", "SynthesisResult", "BatchKModel", "install_into_reference", "lpt_partition", "micro_batches", "wav_float32_bytes", "wav_base64", "TTSServiceManager", "ReferencePolicyManager", "TaskStatus", "TTSTask",
            "PRECISION_FP32", "PRECISION_BF16", "PRECISION_FP16", "PRECISION_FP32_FFMA"]

@@ -80,7 +80,7 @@ def voice_row(pack: torch.Tensor, n_symbols: int) -> torch.Tensor:
 class TTSServiceManager:
     def __init__(self, model, voices: Mapping[str, torch.Tensor], *, token_budget: int = 3200, max_batch_items: int = 64,
                  max_wait_time: float = 0.0, g2p: Optional[Callable[[str], Sequence[str]]] = None,
-                 load_voice: Optional[Callable[[str], torch.Tensor]] = None):
+                 load_voice: Optional[Callable[[str], torch.Tensor]] = None, output_dir: Optional[str] = None):
         """``model.forward_batch(list[str], ref_s [B,1,256], speeds) -> list[Tensor]`` is ``BatchKModel`` (or a stand-in in
         tests).  ``voices``: voice id -> pack [510,1,256]; ``load_voice(voice_id)`` (the reference's ``pipeline.load_voice``,
         pipeline.py:78-109, which fills its ``voices`` dict on demand and raises ValueError for an unknown id) is called for an id
@@ -101,6 +101,11 @@ class TTSServiceManager:
             logger.warning("TTSServiceManager: the model runs with padded_lstm=True: a request's durations depend on its batch; "
                            "construct BatchKModel(..., padded_lstm=False) for batch-invariant results")
         self.task_ttl = 3600.0                             # finished tasks are forgotten after this many seconds (evict_finished)
+        # The reference writes every finished task to <output_dir>/<task_id>.wav (service.py:318-321, 373-404) and its endpoint
+        # re-reads that file (api/endpoints.py:125-150).  With an output_dir the same file appears here (same float32 RIFF layout,
+        # egress.py) so that endpoint keeps working unchanged; without one nothing touches the disk and task_wav_bytes() /
+        # task_wav_base64() give the endpoint's payload straight from memory.
+        self.output_dir = output_dir
         self.model = model
         self.voices = voices
         self.token_budget = token_budget
@@ -233,6 +238,53 @@ class TTSServiceManager:
                 break
         return batch
 
+    @classmethod
+    def from_reference(cls, repo_id: str, voices_dir: str, device: Optional[str] = None, batch_size: int = 4, max_wait_time: float = 0.2,
+                       chunk_size: int = 200, output_dir: Optional[str] = None, **kw) -> "TTSServiceManager":
+        """The reference's own constructor signature (core/service.py:47-56).  Builds the reference's ``CachedTTSPipeline`` - its text
+        normalisation, G2P and voice loading, unchanged - with the B200 engine installed in the ``BatchKModel`` slot
+        (kmodel.install_into_reference), and puts this manager's batcher in front of it.  ``batch_size`` and ``chunk_size`` are the
+        reference's knobs for ITS batcher (at most 4 tasks per call, never read respectively); the token budget replaces them
+        (``token_budget=`` in ``kw``)."""
+        from .kmodel import install_into_reference
+        install_into_reference()
+        from illufly_tts.core.pipeline import CachedTTSPipeline            # the reference's, resolved with the stand-in model class
+        pipeline = CachedTTSPipeline(repo_id, voices_dir, device)
+
+        def g2p(text: str):                                                # what pipeline.process(segment_text=True) does per segment (:400-413)
+            norm = pipeline.preprocess_text(text)
+            return [pipeline.phonemes_to_ipa(pipeline.text_to_phonemes(seg)) for seg in pipeline.segment_text(norm)]
+        mgr = cls(pipeline.model, pipeline.voices, g2p=g2p, load_voice=pipeline.load_voice, max_wait_time=0.0, output_dir=output_dir, **kw)
+        mgr.pipeline = pipeline
+        mgr.batch_size, mgr.chunk_size, mgr.reference_max_wait_time = batch_size, chunk_size, max_wait_time
+        return mgr
+
+    # ---- audio egress (SURVEY 8(f) row 2) ------------------------------------------------------------------------
+    def task_audio(self, task_id: str) -> torch.Tensor:
+        """the finished task's waveform: its chunks concatenated (pipeline.py:420), on the host"""
+        t = self.tasks[task_id]
+        if t.status != TaskStatus.COMPLETED or not t.audio_chunks:
+            raise ValueError(f"task {task_id} has no audio (status {t.status.value})")
+        return torch.cat([c.reshape(-1).cpu() for c in t.audio_chunks])
+
+    def task_wav_bytes(self, task_id: str) -> bytes:
+        """the file the reference would have written for this task (service.py:373-404), in memory"""
+        from .egress import wav_float32_bytes
+        return wav_float32_bytes(self.task_audio(task_id))
+
+    def task_wav_base64(self, task_id: str) -> str:
+        """the ``audio_base64`` field of the reference's endpoint response (api/endpoints.py:150-158)"""
+        from .egress import wav_base64
+        return wav_base64(self.task_audio(task_id))
+
+    def _write_output(self, t: TTSTask) -> None:
+        import os
+        from .egress import wav_float32_bytes
+        os.makedirs(self.output_dir, exist_ok=True)
+        blob = wav_float32_bytes(torch.cat([c.reshape(-1).cpu() for c in t.audio_chunks]))
+        with open(os.path.join(self.output_dir, f"{t.task_id}.wav"), "wb") as f:
+            f.write(blob)
+
     def evict_finished(self, now: Optional[float] = None) -> int:
         """forget COMPLETED / FAILED / CANCELED tasks older than ``task_ttl`` (the reference keeps every task for ever); called
         once per batch round, so ``tasks`` - which select_batch scans - stays proportional to the live load"""
@@ -309,7 +361,14 @@ class TTSServiceManager:
                     t.error = str(bad) if bad is not None else "the engine returned too few waveforms"
                 else:
                     t.audio_chunks.extend(mine)
-                    t.status = TaskStatus.COMPLETED
+                    if self.output_dir:                     # the file the reference's endpoint re-reads: on disk BEFORE the task shows as done
+                        try:
+                            await asyncio.to_thread(self._write_output, t)
+                        except Exception as exc:
+                            t.status = TaskStatus.FAILED
+                            t.error = f"could not write the audio file: {exc}"
+                    if t.status != TaskStatus.FAILED:
+                        t.status = TaskStatus.COMPLETED
                 t.completed_at = time.time()
 
 

@@ -313,3 +313,60 @@ def test_service_forces_strict_and_evicts_finished_tasks():
     assert svc.tasks[tid].status == pkg.TaskStatus.COMPLETED
     assert svc.evict_finished(now=svc.tasks[tid].completed_at + 10) == 0 and tid in svc.tasks
     assert svc.evict_finished(now=svc.tasks[tid].completed_at + svc.task_ttl + 1) == 1 and tid not in svc.tasks
+
+
+def test_service_audio_egress_and_reference_constructor(tmp_path, monkeypatch):
+    """SURVEY 8(f) row 2 + the reference's constructor signature (service.py:47-56): from_reference() builds the reference's
+    pipeline class (here a stand-in module with the methods the manager uses) around the installed BatchKModel slot; a finished task
+    is available as the float32 RIFF image the reference's endpoint returns - from memory, and as <output_dir>/<task_id>.wav"""
+    import asyncio
+    import sys
+    import types
+
+    from illufly_tts_b200.egress import read_wav_float32
+
+    class FakeModel:
+        strict = True
+        padded_lstm = False
+
+        def forward_batch(self, ph, ref, speeds=None):
+            return [torch.full((600 * len(p),), 0.01 * len(p)) for p in ph]
+
+    class FakePipeline:                                   # the surface of the reference's CachedTTSPipeline that the manager touches
+        def __init__(self, repo_id, voices_dir, device=None):
+            self.model, self.voices, self.args = FakeModel(), {}, (repo_id, voices_dir, device)
+
+        def load_voice(self, vid):
+            self.voices[vid] = torch.zeros(510, 1, 256)
+            return self.voices[vid]
+
+        def preprocess_text(self, text): return text.strip()
+        def segment_text(self, text): return [s for s in text.split("|") if s]
+        def text_to_phonemes(self, seg): return seg.lower()
+        def phonemes_to_ipa(self, ph): return ph + "ipa"
+    mod = types.ModuleType("illufly_tts.core.pipeline")
+    mod.CachedTTSPipeline = FakePipeline
+    for name in ("illufly_tts", "illufly_tts.core"):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    monkeypatch.setitem(sys.modules, "illufly_tts.core.pipeline", mod)
+
+    async def main():
+        svc = pkg.TTSServiceManager.from_reference("repo", "voices", "cuda:0", batch_size=4, max_wait_time=0.2, chunk_size=200, output_dir=str(tmp_path))
+        assert svc.pipeline.args == ("repo", "voices", "cuda:0") and sys.modules["illufly_tts.core.kmodel"].BatchKModel is pkg.BatchKModel
+        tid = await svc.submit_task("Hello wor|ld again", "zf_001")
+        await svc.start()
+        async for _ in svc.stream_result(tid):
+            pass
+        await svc.stop()
+        return svc, tid
+    svc, tid = asyncio.run(main())
+    t = svc.tasks[tid]
+    assert t.status == pkg.TaskStatus.COMPLETED and t.chunks == ["hello woripa", "ld againipa"]
+    blob = svc.task_wav_bytes(tid)
+    audio, sr = read_wav_float32(blob)
+    assert sr == 24000 and audio.numel() == 600 * (12 + 11) and torch.equal(audio, svc.task_audio(tid))
+    on_disk = (tmp_path / f"{tid}.wav").read_bytes()
+    assert on_disk[:60] == blob[:60] and on_disk[64:] == blob[64:]           # identical but for the PEAK time stamp
+    import base64
+    assert base64.b64decode(svc.task_wav_base64(tid))[:4] == b"RIFF"
+    sys.modules.pop("illufly_tts.core.kmodel", None)
