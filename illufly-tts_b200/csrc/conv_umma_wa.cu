@@ -451,6 +451,12 @@ bool make_wplan(const ConvArgs& a, WPlan& pl) {
   const uint32_t limit = 227u * 1024u;
   // three weight stages (3 x 4 MMAs x 128 cycles of cover for one L2 round trip), then the ring, then more weight stages
   pl.nstage = 3;
+  // experiment knobs: fewer weight stages (more ring) for the fp32-input layers with few taps, where the ring starves the producers
+  static const int env_ns = getenv("TTSB_WA_NSTAGE") ? atoi(getenv("TTSB_WA_NSTAGE")) : 3;
+  static const int env_kmax = getenv("TTSB_WA_NSTAGE_KMAX") ? atoi(getenv("TTSB_WA_NSTAGE_KMAX")) : 0;
+  static const int env_rps = getenv("TTSB_WA_RPS") ? atoi(getenv("TTSB_WA_RPS")) : 0;
+  if (!a.x_f16 && a.k <= env_kmax && env_ns >= 2 && env_ns <= 3) pl.nstage = env_ns;
+  const int nstage_min = pl.nstage;
   if (off + pl.nstage * WSTAGE_BYTES > limit) return false;
   const uint32_t left = limit - off - pl.nstage * WSTAGE_BYTES;
   static const bool noring = getenv("TTSB_UMMA_NORING") != nullptr;
@@ -458,7 +464,7 @@ bool make_wplan(const ConvArgs& a, WPlan& pl) {
   // at least two such slots fit, else one
   pl.rps = 2;
   pl.raw_bytes = (uint32_t)(2 * RPP) * pl.row_bytes;
-  if (left / pl.raw_bytes < 2) { pl.rps = 1; pl.raw_bytes = (uint32_t)RPP * pl.row_bytes; }
+  if (left / pl.raw_bytes < 2 || (env_rps == 1 && !a.x_f16)) { pl.rps = 1; pl.raw_bytes = (uint32_t)RPP * pl.row_bytes; }
   pl.rch = pl.rps * RPP;
   pl.nraw = (int)std::min<uint32_t>(left / pl.raw_bytes, (uint32_t)MAXRAW);
   if (pl.nraw < 2 || noring) pl.nraw = 0;
@@ -466,6 +472,7 @@ bool make_wplan(const ConvArgs& a, WPlan& pl) {
   pl.off_raw = off; off += pl.nraw * pl.raw_bytes;
   pl.off_w = off;
   while (pl.nstage < MAXSTAGE && pl.off_w + (pl.nstage + 1) * WSTAGE_BYTES <= limit) ++pl.nstage;
+  (void)nstage_min;
   pl.smem_bytes = pl.off_w + pl.nstage * WSTAGE_BYTES;
   pl.items = a.ntiles;
   return pl.smem_bytes <= limit;
