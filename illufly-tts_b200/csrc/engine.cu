@@ -931,6 +931,33 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   e.d_row2segT = const_cast<int*>(d_r2s);
   const SegTab& tT = e.tabT;
 
+  // ---- text_encoder (A.9): independent of everything up to the length regulation - it runs on the engine's second stream beside
+  // ALBERT and the duration path (whose launches fill 20-120 SMs each) and is joined before the durations are copied out ----
+  static const bool one_stream_b = getenv("TTSB_ONE_STREAM") != nullptr;
+  Run r2(r, one_stream_b ? r.s : e.stream2);
+  if (!one_stream_b) {
+    CK(cudaEventRecord(e.ev_fork, r.s));
+    CK(cudaStreamWaitEvent(e.stream2, e.ev_fork, 0));
+  }
+  {
+    float* TE0 = r.alloc<float>((size_t)R * 512);
+    float* TE1 = r.alloc<float>((size_t)R * 512);
+    float* TEN = r.alloc<float>((size_t)R * 512);
+    float* GX2 = r.alloc<float>((size_t)R * 2048);          // its own gate scratch: the duration path's LSTMs run at the same time
+    if (!TE0 || !TE1 || !TEN || !GX2) return TTSB_E_NOMEM;
+    CK(launch_embedding(d_ids, e.te_emb, 512, TE0, 512, R, r2.s));
+    for (int l = 0; l < 3; ++l) {
+      ConvCall c; c.w = &e.te_cnn[l]; c.x = TE0; c.ldx = 512; c.y = TE1; c.ldy = 512; c.pad = 2; c.exact = true;
+      RC(run_conv(r2, c, tT));
+      e.prof.begin(r2.s, PROF_LAYERNORM, 0.0, 8.0 * (double)(R) * (double)(512));
+      CK(launch_layernorm(TE1, 512, nullptr, 0, TE0, 512, R, 512, 1e-5f, 0, e.te_ln_g[l], e.te_ln_b[l], nullptr, 0, nullptr, ACT_LRELU, 0.2f, r2.s));
+      e.prof.end(r2.s);
+    }
+    RC(run_bilstm(r2, e.te_lstm, TE0, 512, GX2, TEN, 512, tTf, d_ls, n_ls, true));
+    e.d_ten = TEN;
+    if (!one_stream_b) CK(cudaEventRecord(e.ev_join, e.stream2));
+  }
+
   // ---- style projections of the prosody half (AdaLayerNorm + F0/N AdaIN) ----
   RC(run_style(r, e.style_pred, d_ref + 128, 256, B, &e.d_gbP));
   const int ldP = e.style_pred.ldw;
@@ -994,6 +1021,8 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   CK(launch_duration(logits, 52, 50, d_r2s, d_speed, d_dur, d_pd, R, r.s));
   const int* d_used = d_forced ? d_forced : d_pd;
   CK(launch_dur_scan(d_used, tT.segs, B, d_cum, d_tot, r.s));
+  if (!one_stream_b) CK(cudaStreamWaitEvent(r.s, e.ev_join, 0));       // the text encoder (second stream) is part of this half
+  RC(r.tap("t_en", e.d_ten, R, 512, 512));
   // results the host needs to size the frame side: through PINNED memory, so that the copies are asynchronous and the text
   // encoder queued below really overlaps the host's wait (a D2H copy into pageable memory blocks the calling thread)
   const size_t out_bytes = sizeof(int) * (size_t)R + sizeof(float) * (size_t)R + sizeof(int) * (size_t)B + sizeof(unsigned int) + 64;
@@ -1015,22 +1044,6 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   CK(cudaEventRecord(e.ev0, r.s));
   e.d_pred_dur = d_pd; e.d_cum = d_cum;
 
-  // ---- text_encoder (A.9) — queued behind the copies so it overlaps the host wait ----
-  float* TE0 = r.alloc<float>((size_t)R * 512);
-  float* TE1 = r.alloc<float>((size_t)R * 512);
-  float* TEN = r.alloc<float>((size_t)R * 512);
-  if (!TE0 || !TE1 || !TEN) return TTSB_E_NOMEM;
-  CK(launch_embedding(d_ids, e.te_emb, 512, TE0, 512, R, r.s));
-  for (int l = 0; l < 3; ++l) {
-    ConvCall c; c.w = &e.te_cnn[l]; c.x = TE0; c.ldx = 512; c.y = TE1; c.ldy = 512; c.pad = 2; c.exact = true;
-    RC(run_conv(r, c, tT));
-    r.e.prof.begin(r.s, PROF_LAYERNORM, 0.0, 8.0 * (double)(R) * (double)(512));
-    CK(launch_layernorm(TE1, 512, nullptr, 0, TE0, 512, R, 512, 1e-5f, 0, e.te_ln_g[l], e.te_ln_b[l], nullptr, 0, nullptr, ACT_LRELU, 0.2f, r.s));
-    r.e.prof.end(r.s);
-  }
-  RC(run_bilstm(r, e.te_lstm, TE0, 512, GX, TEN, 512, tTf, d_ls, n_ls, true));
-  RC(r.tap("t_en", TEN, R, 512, 512));
-  e.d_ten = TEN;
   static const bool gap_prof = getenv("TTSB_GAP_PROF") != nullptr;
   if (gap_prof) {                       // the last work of this half: the text encoder, queued to overlap the host's part
     if (!e.ev_gap0) { CK(cudaEventCreate(&e.ev_gap0)); CK(cudaEventCreate(&e.ev_gap1)); }
