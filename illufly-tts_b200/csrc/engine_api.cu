@@ -381,6 +381,7 @@ int ttsb_op_conv1d(ttsb_engine* h, const float* x, const float* w, const float* 
   }
   if (!tensor) { a.wb = nullptr; a.wfmt = 0; a.sat = nullptr; }
   if (reps < 1) reps = 1;
+  if (a.sat) CKA(cudaMemsetAsync(a.sat, 0, sizeof(unsigned int), e.stream));
   OpTimer tm(e, ms);
   CKA(tm.start());
   for (int i = 0; i < reps; ++i) {
@@ -389,6 +390,11 @@ int ttsb_op_conv1d(ttsb_engine* h, const float* x, const float* w, const float* 
   CKA(tm.stop());
   if (ms) *ms /= (float)reps;
   CKA(cudaStreamSynchronize(e.stream));
+  if (a.sat) {      // the split-fp16 path's range check, as the engine does after every step of the strict tier
+    unsigned int n_sat = 0;
+    CKA(cudaMemcpy(&n_sat, a.sat, sizeof(n_sat), cudaMemcpyDeviceToHost));
+    if (n_sat) { set_error("op_conv1d: %u operand conversions left fp16's range (|x| > 4094) in the split-fp16 path", n_sat); return TTSB_E_RANGE; }
+  }
   return TTSB_OK;
 } GUARD_END("op_conv1d")
 

@@ -482,6 +482,35 @@ def test_op_conv1d_both_kernels(engine, Cin, Cout, k, d):
     assert float((yh - ref(x, w)).abs().max()) < 6e-3
 
 
+def test_split_path_range_is_checked_not_assumed(engine):
+    """the fp32-class tensor-core path (x = hi + lo in fp16, operands scaled) has a range: activations beyond +-4094 would saturate.
+    Large WEIGHTS are fine (the scale is chosen per layer from max|w|: a fixed 256 used to turn |w| >= 256 into inf); large
+    ACTIVATIONS are counted on the device and the call fails with E_RANGE instead of returning a silently wrong result"""
+    g = torch.Generator().manual_seed(8)
+    off = [0, 200]
+    x = torch.randn(200, 128, generator=g)
+    w = torch.randn(128, 128, 3, generator=g) / 20
+    b = torch.randn(128, generator=g)
+
+    def ref(xx, ww):
+        return torch.nn.functional.conv1d(xx.t()[None].double(), ww.double(), b.double(), padding=1)[0].t().float()
+    big_w = w * 4000                                                # |w| up to ~600
+    y = engine.op_conv1d(x.cuda(), big_w, b, off, 1, pkg.PRECISION_FP32).cpu()
+    r = ref(x, big_w)
+    assert float((y - r).abs().max()) < 2e-6 * float(r.abs().max()) + 1e-4
+    small_w = w * 1e-4
+    y = engine.op_conv1d(x.cuda(), small_w, None, off, 1, pkg.PRECISION_FP32).cpu()
+    r = torch.nn.functional.conv1d(x.t()[None].double(), small_w.double(), None, padding=1)[0].t().float()
+    assert float((y - r).abs().max()) < 2e-6 * float(r.abs().max())
+    ok = engine.op_conv1d((x.clamp(-3.9, 3.9) * 1000).cuda(), w, b, off, 1, pkg.PRECISION_FP32)     # |x| <= 3900: inside the range
+    assert torch.isfinite(ok).all()
+    with pytest.raises(pkg._lib.EngineError) as ei:
+        engine.op_conv1d((x * 3000).cuda(), w, b, off, 1, pkg.PRECISION_FP32)
+    assert ei.value.code == pkg._lib.E_RANGE
+    y = engine.op_conv1d((x * 3000).cuda(), w, b, off, 1, pkg.PRECISION_FP32_FFMA).cpu()  # the CUDA-core mode has no such range
+    assert float((y - ref(x * 3000, w)).abs().max()) < 1e-5 * 3000 * 3
+
+
 def test_op_bilstm_matches_torch(engine):
     torch.manual_seed(4)
     lstm = torch.nn.LSTM(640, 256, 1, batch_first=True, bidirectional=True)
