@@ -52,7 +52,7 @@ struct ConvArgs {
   double* ostats; int ld_ostats;       // [nseg][ld_ostats][2]
   const Seg* segs; const Tile* tiles; int ntiles; int tile_rows;
   uint8_t* xpack; size_t xpack_bytes;  // scratch for the pre-packed split-fp16 operand images of k=1 layers (conv_umma.cu), or null
-  int x_f16, y_f16;                    // conv_umma_wa.cu only: x / y point to fp16 rows (the c1 -> c2 intermediate of a resblock), ldx / ldy in elements
+  int x_f16, y_f16, r_f16;             // conv_umma_wa.cu only: x / y / res point to fp16 rows (the intermediates of a resblock), ld* in elements
   float split_wscale;                  // wfmt 2: the power of two the weights of this layer were scaled by at pack time
   unsigned int* sat;                   // wfmt 2: device counter of operand conversions that left fp16's range (|16 x| > 65504), or null
 };

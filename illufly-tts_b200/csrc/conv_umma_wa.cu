@@ -69,16 +69,20 @@ struct WArgs {
 // time); with units of 16 rows requested one unit ahead, at 8 x ~2.2 k cycles (the load latency under this kernel's own traffic).
 // FULL: the half tile lies inside the utterance - straight-line code; otherwise rows past the utterance's end are predicated.
 //   y = (acc + bias [+ res]) [* os] [+ y_old]; dsum / dsq += this thread's sum / sum of squares of what it stored
-template <bool RES, bool SCALE, bool ACC, bool YH, bool FULL>
+// RES: 0 = no residual, 1 = fp32 residual rows, 2 = fp16 residual rows (the block's running value between its iterations)
+template <int RES, bool SCALE, bool ACC, bool YH, bool FULL>
 __device__ __forceinline__ void epi_tile(const uint32_t tacc, const int nv, const float bias, const float os, float* __restrict__ yb, __half* __restrict__ yh,
-                                         const float* __restrict__ rb, const uint32_t bar_empty, const int lane, double& dsum, double& dsq) {
+                                         const void* __restrict__ rbv, const uint32_t bar_empty, const int lane, double& dsum, double& dsq) {
+  const float* __restrict__ rb = reinterpret_cast<const float*>(rbv);
+  const __half* __restrict__ rh = reinterpret_cast<const __half*>(rbv);
   constexpr size_t ldy = CH, ldr = CH;             // rows of y and res are whole channel rows (conv_umma_wa_supported): the row offsets
                                                    // below are immediates of the load / store instructions, not address registers
   constexpr int W = ACC ? 16 : 32;                 // window depth per stream (two streams when the old output is read too)
   float rw[W], yw[ACC ? W : 1];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    if (RES) rw[i] = (FULL || i < nv) ? rb[(size_t)i * ldr] : 0.f;
+    if (RES == 1) rw[i] = (FULL || i < nv) ? rb[(size_t)i * ldr] : 0.f;
+    if (RES == 2) rw[i] = (FULL || i < nv) ? __half2float(rh[(size_t)i * ldr]) : 0.f;
     if (ACC) yw[i] = (FULL || i < nv) ? yb[(size_t)i * ldy] : 0.f;
   }
   uint32_t v[16];
@@ -100,7 +104,8 @@ __device__ __forceinline__ void epi_tile(const uint32_t tacc, const int nv, cons
     else if (SCALE) o *= os;
     else if (ACC) o += yw[i % W];
     if (i + W < 128) {                             // refill the slots just consumed: row i + W
-      if (RES) rw[i % W] = (FULL || i + W < nv) ? rb[(size_t)(i + W) * ldr] : 0.f;
+      if (RES == 1) rw[i % W] = (FULL || i + W < nv) ? rb[(size_t)(i + W) * ldr] : 0.f;
+      if (RES == 2) rw[i % W] = (FULL || i + W < nv) ? __half2float(rh[(size_t)(i + W) * ldr]) : 0.f;
       if (ACC) yw[i % W] = (FULL || i + W < nv) ? yb[(size_t)(i + W) * ldy] : 0.f;
     }
     if (YH) {
@@ -117,8 +122,8 @@ __device__ __forceinline__ void epi_tile(const uint32_t tacc, const int nv, cons
   }
 }
 
-template <bool RES, bool SCALE, bool ACC, bool YH>
-__device__ __forceinline__ void epi_tile_any(const uint32_t tacc, const int nv, const float bias, const float os, float* yb, __half* yh, const float* rb,
+template <int RES, bool SCALE, bool ACC, bool YH>
+__device__ __forceinline__ void epi_tile_any(const uint32_t tacc, const int nv, const float bias, const float os, float* yb, __half* yh, const void* rb,
                                              const uint32_t bar_empty, const int lane, double& dsum, double& dsq) {
   if (nv >= 128) epi_tile<RES, SCALE, ACC, YH, true>(tacc, 128, bias, os, yb, yh, rb, bar_empty, lane, dsum, dsq);
   else epi_tile<RES, SCALE, ACC, YH, false>(tacc, nv, bias, os, yb, yh, rb, bar_empty, lane, dsum, dsq);
@@ -358,8 +363,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
         }
         if (p.res) {
           const int nr = min(TN, sg.out_len - tl.t0);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.res + (size_t)(sg.out_off + tl.t0) * p.ldr);
-          const uint32_t bytes = (uint32_t)nr * (uint32_t)p.ldr * 4u;
+          const uint32_t rsz = p.r_f16 ? 2u : 4u;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.res) + (size_t)(sg.out_off + tl.t0) * p.ldr * rsz;
+          const uint32_t bytes = (uint32_t)nr * (uint32_t)p.ldr * rsz;
           for (uint32_t o = 0; o < bytes; o += 16384u) prefetch_l2(src + o, min(16384u, bytes - o));
         }
         if (p.accumulate && !YH) {                    // the running sum of the three parallel resblocks is read back too
@@ -412,12 +418,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
       const size_t row0 = (size_t)(seg.out_off + tbase);
       float* yb = YH ? nullptr : p.y + row0 * ldy + c;
       __half* yh = YH ? reinterpret_cast<__half*>(p.y) + row0 * ldy + c : nullptr;
-      const float* rb = has_res ? p.res + row0 * ldr + c : nullptr;
+      // residual rows: fp32 (the stage's input, first iteration of a block) or fp16 (the block's running value)
+      const void* rb = !has_res ? nullptr
+                       : p.r_f16 ? static_cast<const void*>(reinterpret_cast<const __half*>(p.res) + row0 * ldr + c)
+                                 : static_cast<const void*>(p.res + row0 * ldr + c);
       const uint32_t be = bar_acc_empty(slot);
-      if (YH) epi_tile_any<false, false, false, true>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
-      else if (has_res && acc) epi_tile_any<true, true, true, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
-      else if (has_res && sc) epi_tile_any<true, true, false, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
-      else epi_tile_any<true, false, false, false>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);      // fp32 output always has a residual (supported())
+      if (YH) {                        // c1 (no residual) and the c2 of a block's first two iterations (running value out as fp16)
+        if (!has_res) epi_tile_any<0, false, false, true>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
+        else if (p.r_f16) epi_tile_any<2, false, false, true>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
+        else epi_tile_any<1, false, false, true>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
+      } else if (p.r_f16) {            // the c2 of a block's last iteration: fp32 out (scaled, accumulated over the parallel blocks)
+        if (acc) epi_tile_any<2, true, true, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
+        else if (sc) epi_tile_any<2, true, false, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
+        else epi_tile_any<2, false, false, false>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
+      } else {
+        if (acc) epi_tile_any<1, true, true, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
+        else if (sc) epi_tile_any<1, true, false, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
+        else epi_tile_any<1, false, false, false>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
+      }
       if (p.ostats) {
         // flush this thread's running sums when the utterance changes or the CTA is done
         const bool flush = item + 1 >= item1 || p.tiles[item + 1].seg != tile.seg;
@@ -490,8 +508,10 @@ bool conv_umma_wa_supported(const ConvArgs& a) {
   if (a.tile_rows != TN || a.ldx != CH || a.ldy != CH || (a.res && a.ldr != CH)) return false;
   if (a.acc_scale != 0.f && a.acc_scale != 1.0f) return false;
   if (reinterpret_cast<uintptr_t>(a.x) & 15) return false;
-  if (a.y_f16 && (a.res || a.accumulate || a.out_scale != 1.0f)) return false;
-  if (!a.y_f16 && !a.res) return false;        // the two shapes of an AdaINResBlock1: c1 (fp16 out, plain) and c2 (fp32 out + residual)
+  if (a.y_f16 && (a.accumulate || a.out_scale != 1.0f)) return false;
+  if (!a.y_f16 && !a.res) return false;        // the shapes of an AdaINResBlock1: c1 (fp16 out, plain), c2 (+ residual; fp16 or fp32 out)
+  if (a.r_f16 && !a.res) return false;
+  if (a.res && (reinterpret_cast<uintptr_t>(a.res) & 1)) return false;
   if (!a.pstats || !a.gb || !a.alpha) return false;
   WPlan pl;
   return make_wplan(a, pl);
@@ -504,10 +524,11 @@ cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
   u.a = a;
   if (!make_wplan(a, u.p)) return cudaErrorInvalidValue;
   using KernelFn = void (*)(const WArgs);
-  // [wfmt][x_f16][y_f16]; an fp16 input with an fp16 output does not occur (c1 reads the fp32 residual stream, c2 writes it)
+  // [wfmt][x_f16][y_f16]: fp32 in / fp16 out = c1 of a block's first iteration; fp16 / fp16 = the other c1s and the c2s that write the
+  // block's running value; fp16 in / fp32 out = the last c2; fp32 / fp32 does not occur
   static const KernelFn table[2][2][2] = {
-      {{conv_umma_wa_kernel<0, false, false>, conv_umma_wa_kernel<0, false, true>}, {conv_umma_wa_kernel<0, true, false>, nullptr}},
-      {{conv_umma_wa_kernel<1, false, false>, conv_umma_wa_kernel<1, false, true>}, {conv_umma_wa_kernel<1, true, false>, nullptr}}};
+      {{nullptr, conv_umma_wa_kernel<0, false, true>}, {conv_umma_wa_kernel<0, true, false>, conv_umma_wa_kernel<0, true, true>}},
+      {{nullptr, conv_umma_wa_kernel<1, false, true>}, {conv_umma_wa_kernel<1, true, false>, conv_umma_wa_kernel<1, true, true>}}};
   const KernelFn kernel = table[a.wfmt][a.x_f16 ? 1 : 0][a.y_f16 ? 1 : 0];
   if (!kernel) return cudaErrorInvalidValue;
   int dev = 0;

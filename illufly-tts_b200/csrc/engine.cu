@@ -542,7 +542,7 @@ struct ConvCall {
   bool tensor = false;           // eligible for the tcgen05 path (16-bit operands) when the engine runs in a tensor precision
   bool exact = false;            // text side: tcgen05 with split-fp16 operands (fp32-equivalent) in tensor precisions, FFMA in FP32
   bool wa = false;               // 128-channel layer on the weights-as-A kernel (conv_umma_wa.cu); the table has 256-row tiles
-  bool x_f16 = false, y_f16 = false;   // wa only: x / y are fp16 rows (the c1 -> c2 intermediate of a resblock)
+  bool x_f16 = false, y_f16 = false, r_f16 = false;   // wa only: x / y / res are fp16 rows (the intermediates of a resblock)
 };
 
 // Which kernel a convolution runs on, by precision mode:
@@ -572,11 +572,12 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   a.segs = t.segs; a.tiles = t.tiles; a.ntiles = t.ntiles; a.tile_rows = 128;
   if (c.wa) {
     // the caller sized its buffers for this kernel (fp16 intermediate, 256-row tiles): no other kernel can take the call
-    a.tile_rows = CONV_WA_TILE_ROWS; a.x_f16 = c.x_f16; a.y_f16 = c.y_f16;
+    a.tile_rows = CONV_WA_TILE_ROWS; a.x_f16 = c.x_f16; a.y_f16 = c.y_f16; a.r_f16 = c.r_f16;
     if (!half16 || !conv_umma_wa_supported(a)) { set_error("internal: weights-as-A conv kernel refused Cin=%d Cout=%d k=%d dil=%d", a.Cin, a.Cout, a.k, a.dil); return TTSB_E_INVALID; }
     const double rows_wa = (double)t.out_rows;
     r.e.prof.begin(r.s, PROF_CONV_TENSOR, 2.0 * rows_wa * a.Cin * a.Cout * a.k,
-                   rows_wa * a.Cout * ((a.y_f16 ? 2.0 : 4.0) + (a.res ? 4.0 : 0.0) + (a.accumulate ? 4.0 : 0.0)) + (a.x_f16 ? 2.0 : 4.0) * (double)t.in_rows * a.Cin);
+                   rows_wa * a.Cout * ((a.y_f16 ? 2.0 : 4.0) + (a.res ? (a.r_f16 ? 2.0 : 4.0) : 0.0) + (a.accumulate ? 4.0 : 0.0)) +
+                       (a.x_f16 ? 2.0 : 4.0) * (double)t.in_rows * a.Cin);
     CK(launch_conv_umma_wa(a, r.s));
     r.e.prof.end(r.s);
     return TTSB_OK;
@@ -688,28 +689,34 @@ int run_resblk1d(Run& r, const ResBlk1dW& b, const float* x, int ldx, const doub
 // kokoro AdaINResBlock1.  x (ld C) with statistics xstats; the running value lives in `cur` (ld C; may equal x when
 // the caller allows in-place).  The last of the three iterations writes `(x + xt) * final_scale` into `out` (accumulating if asked).
 int run_resblock1(Run& r, const ResBlock1W& b, const float* x, const double* xstats, float* cur, float* xt, float* out, float final_scale,
-                  int accumulate, double* out_stats, const float* gb, int ld_gb, const SegTab& t, const SegTab* twa = nullptr) {
+                  int accumulate, double* out_stats, const float* gb, int ld_gb, const SegTab& t, const SegTab* twa = nullptr, __half* cur16 = nullptr) {
   const int C = b.C, nseg = t.nseg;
   const float* in = x;
   const double* in_st = xstats;
-  // twa: the 256-row tile table of the weights-as-A kernel; `xt` then holds fp16 rows (it is only ever read as a 16-bit operand)
+  // twa: the 256-row tile table of the weights-as-A kernel.  On that path the block's intermediates are fp16 rows: `xt` (c1 -> c2,
+  // only ever read as a 16-bit operand) and `cur16`, the running value between the three iterations (read as c1's operand and as c2's
+  // residual).  The block's input and its output stay fp32, as do all statistics (taken from the values as stored).
   const bool wa = twa != nullptr;
   const SegTab& tt = wa ? *twa : t;
+  if (wa && !cur16) { set_error("internal: weights-as-A resblock without an fp16 running buffer"); return TTSB_E_INVALID; }
   for (int m = 0; m < 3; ++m) {
     double* st_t = r.stats(nseg, C);
     if (!st_t) return TTSB_E_NOMEM;
-    ConvCall c1; c1.w = &b.c1[m]; c1.x = in; c1.ldx = C; c1.y = xt; c1.ldy = C; c1.dil = b.dil[m]; c1.pad = (b.k * b.dil[m] - b.dil[m]) / 2;
+    const bool in16 = wa && m > 0;                       // the running value of iterations 1, 2 lives in cur16
+    ConvCall c1; c1.w = &b.c1[m]; c1.x = in16 ? reinterpret_cast<const float*>(cur16) : in; c1.ldx = C; c1.y = xt; c1.ldy = C; c1.dil = b.dil[m];
+    c1.pad = (b.k * b.dil[m] - b.dil[m]) / 2;
     c1.pro = PRO_ADAIN_SNAKE; c1.pstats = in_st; c1.gb = gb; c1.ld_gb = ld_gb; c1.ad = b.a1[m]; c1.alpha = b.alpha1[m]; c1.ostats = st_t; c1.tensor = true;
-    c1.wa = wa; c1.y_f16 = wa;
+    c1.wa = wa; c1.y_f16 = wa; c1.x_f16 = in16;
     RC(run_conv(r, c1, tt));
     const bool last = m == 2;
     double* st_n = last ? out_stats : r.stats(nseg, C);
     if (!last && !st_n) return TTSB_E_NOMEM;
     ConvCall c2; c2.w = &b.c2[m]; c2.x = xt; c2.ldx = C; c2.dil = 1; c2.pad = (b.k - 1) / 2;
     c2.pro = PRO_ADAIN_SNAKE; c2.pstats = st_t; c2.gb = gb; c2.ld_gb = ld_gb; c2.ad = b.a2[m]; c2.alpha = b.alpha2[m];
-    c2.res = in; c2.ldr = C; c2.tensor = true;
-    c2.wa = wa; c2.x_f16 = wa;
+    c2.res = in16 ? reinterpret_cast<const float*>(cur16) : in; c2.ldr = C; c2.tensor = true;
+    c2.wa = wa; c2.x_f16 = wa; c2.r_f16 = in16;
     if (last) { c2.y = out; c2.ldy = C; c2.out_scale = final_scale; c2.accumulate = accumulate; c2.ostats = out_stats; }
+    else if (wa) { c2.y = reinterpret_cast<float*>(cur16); c2.ldy = C; c2.y_f16 = true; c2.ostats = st_n; }
     else { c2.y = cur; c2.ldy = C; c2.ostats = st_n; }
     RC(run_conv(r, c2, tt));
     in = cur; in_st = st_n;
@@ -793,12 +800,16 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
     float* b3 = r.alloc<float>(n);
     double* st_xs = r.stats(nseg, C);
     if (!b0 || !b1 || !b2 || !b3 || !st_xs) return TTSB_E_NOMEM;
+    // the blocks' running value between iterations (fp16 on the weights-as-A path) lives in whichever buffer is idle: x0's while
+    // noise_res runs (x0 is written by the upsample-add after it), cur's while the three parallel resblocks run
+    __half* c16_noise = twa ? reinterpret_cast<__half*>(b3) : nullptr;
+    __half* c16_res = twa ? reinterpret_cast<__half*>(b2) : nullptr;
     // x_source = noise_res[i](noise_convs[i](har))
     float *xs = b0, *xt = b1, *xs2 = b2;
     ConvCall cn; cn.x = har; cn.y = xs; cn.ldy = C; cn.ostats = st_xs; cn.tensor = true;
     if (i == 0) { cn.w = &e.noise_conv0r; cn.ldx = 144; cn.pad = 1; RC(run_conv(r, cn, tHb_S0)); }
     else { cn.w = &e.noise_conv[1]; cn.ldx = 24; RC(run_conv(r, cn, tH_S1)); }
-    RC(run_resblock1(r, e.noise_res[i], xs, st_xs, xs, xt, xs2, 1.0f, 0, nullptr, gbD, ld_gb, tS, twa));
+    RC(run_resblock1(r, e.noise_res[i], xs, st_xs, xs, xt, xs2, 1.0f, 0, nullptr, gbD, ld_gb, tS, twa, c16_noise));
     // x = ups[i](leaky_relu(x, 0.1))  (+ ReflectionPad1d((1,0)) for the last stage) + x_source
     float *up = b0, *x0 = b3;
     double* st_x0 = r.stats(nseg, C);
@@ -812,7 +823,7 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
     // mean of the three parallel AdaINResBlock1
     float *acc = b0, *cur = b2;
     for (int j = 0; j < 3; ++j)
-      RC(run_resblock1(r, e.resblk[3 * i + j], x0, st_x0, cur, xt, acc, 1.0f / 3.0f, j > 0, nullptr, gbD, ld_gb, tS, twa));
+      RC(run_resblock1(r, e.resblk[3 * i + j], x0, st_x0, cur, xt, acc, 1.0f / 3.0f, j > 0, nullptr, gbD, ld_gb, tS, twa, c16_res));
     r.release_to(stage_scope);
     RC(r.tap(i == 0 ? "gen_stage0" : "gen_stage1", acc, spS.total, C, C));
     xin = acc;
