@@ -507,7 +507,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           b += lead; bytes = (bytes - lead) & ~size_t(15);
           for (size_t o = 0; o < bytes; o += 16384) prefetch_l2(b + o, (uint32_t)(bytes - o < 16384 ? bytes - o : 16384));
         };
-        if (u.xpack) {
+        if (!(u.l2pf & 1)) {
+        } else if (u.xpack) {
           pf(u.xpack + (size_t)(item % p.ntiles) * pl.nsc * pl.slab_bytes, (size_t)pl.nsc * pl.slab_bytes);
         } else {
           int lo = (tl.t0 - p.pad) >> p.in_shr, hi = ((tl.t0 - p.pad + pl.SR - 1) >> p.in_shr) + 1;
@@ -516,6 +517,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
         }
         const int nr = min(BM, sg.out_len - tl.t0);
         const int n0 = (item / p.ntiles) * pl.BN;
+        if (!(u.l2pf & 4)) return;
         if (nr > 0 && p.res) {
           if (p.ldr <= pl.BN) pf(p.res + (size_t)(sg.out_off + tl.t0) * p.ldr, (size_t)nr * p.ldr * 4);      // whole rows
           else for (int r = 0; r < nr; ++r) pf(p.res + (size_t)(sg.out_off + tl.t0 + r) * p.ldr + n0, (size_t)min(pl.BN, p.Cout - n0) * 4);
@@ -565,8 +567,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
     const float acs = p.acc_scale != 0.f ? p.acc_scale : 1.0f;
     uint32_t n = 0;
     long long tw_full = 0;
+    long long tp_ld = 0, tp_stage = 0, tp_io = 0, tp_stats = 0, tp_pre = 0, tp_top = 0, tp_post = 0;       // TTSB_UMMA_PROF: where an epilogue chunk's cycles go (warp 0 of the role)
+#ifdef TTSB_EPI_PROF
+    const bool tprof = u.prof != nullptr;
+#else
+    constexpr bool tprof = false;   // the per-phase timers cost registers: build with -DTTSB_EPI_PROF to get them (profiles/r02_epilogue_phases.md)
+#endif
     const long long t_start = clock64();
     for (int item = item0; item < item1; ++item, ++n) {
+      long long ti0 = 0;
+      if (tprof) ti0 = clock64();
       const int nt = item / p.ntiles;
       const Tile tile = p.tiles[item % p.ntiles];
       const Seg seg = p.segs[tile.seg];
@@ -579,24 +589,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
       // cost a full L2 round trip per chunk: ncu put 23 % of the epilogue warps' stall samples on the first FFMA that reads it.
       float4 b4n = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias && n0 + cc + 3 < p.Cout) b4n = *reinterpret_cast<const float4*>(p.bias + n0 + cc);
+      // residual rows: those of the first chunk are requested before the wait for the accumulator, those of chunk c+1 right after
+      // chunk c's stores - ahead of its statistics, the next TMEM load and the staging writes, none of which need these registers.
+      // Requested at the top of their own chunk they arrived ~900 cycles late (profile: +7.5 k cycles per item on every c2 launch).
+      float4 r4[8];
+      if (p.res && tile_fast && n0 + cc + 3 < p.Cout) {
+        const float* rb = p.res + row0 * p.ldr + n0 + cc;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(rb + i * rstep);
+      }
+      if (tprof) tp_pre += clock64() - ti0;
       mbar_wait_t(bar_acc_full(slot), (n >> 1) & 1u, tw_full);
       tc_fence_after();
       const uint32_t tacc = tmem_base + slot * (uint32_t)pl.acc_cols + ((uint32_t)(q * 32) << 16);
       for (int chunk = 0; chunk < nchunk; ++chunk) {
+        long long tc0 = 0;
+        if (tprof) tc0 = clock64();
         const int c0 = chunk * 32;
         const int co = n0 + c0 + cc;
         const float4 b4c = b4n;
         b4n = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias && chunk + 1 < nchunk && co + 32 + 3 < p.Cout) b4n = *reinterpret_cast<const float4*>(p.bias + co + 32);
-        // residual rows of this chunk: requested before the TMEM load and the staging writes below (they do not depend on them)
-        float4 r4[8];
-        const bool chunk_fast = tile_fast && co + 3 < p.Cout;
-        if (p.res && chunk_fast) {
-          const float* rb = p.res + row0 * p.ldr + co;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(rb + i * rstep);
-        }
         uint32_t v[32];
+        long long tq0 = 0;
+        if (tprof) { tq0 = clock64(); tp_top += tq0 - tc0; }
         tmem_ld32(tacc + (uint32_t)c0, v);
         if (WFMT == 2) {
           uint32_t v2[32];
@@ -609,6 +625,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty(slot));      // one arrival per warp (128 lanes on one word serialise)
         }
+        long long tq1 = 0;
+        if (tprof) { tq1 = clock64(); tp_ld += tq1 - tq0; }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           float4 f;
@@ -616,6 +634,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           *reinterpret_cast<float4*>(stg + lane * STG_LD + 4 * i) = f;
         }
         __syncwarp();
+        long long tq2 = 0;
+        if (tprof) { tq2 = clock64(); tp_stage += tq2 - tq1; }
         float ps[4] = {0.f, 0.f, 0.f, 0.f}, pq[4] = {0.f, 0.f, 0.f, 0.f};
         const bool colok = co < p.Cout && !(u.dbg & 2);
         const bool full4 = co + 3 < p.Cout;
@@ -689,24 +709,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           }
         }
         __syncwarp();
-        if (p.ostats) {
+        if (p.res && tile_fast && chunk + 1 < nchunk && co + 32 + 3 < p.Cout) {
+          const float* rb = p.res + row0 * p.ldr + co + 32;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 8);  pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 8);
-            ps[e] += __shfl_xor_sync(0xffffffffu, ps[e], 16); pq[e] += __shfl_xor_sync(0xffffffffu, pq[e], 16);
-          }
-          // after the butterfly every lane holds the totals of its four columns; lane l adds ONE of them (column cc + (l >> 3)):
-          // one owner per (row quadrant, channel), two FP64 adds per chunk with all lanes busy instead of eight on a quarter of
-          // the warp (ncu: 8 % of the epilogue's stall samples sat on the FP64 pipe).  Running sums over this CTA's consecutive tiles.
-          {
-            const int e = lane >> 3;
-            const float vs = e == 0 ? ps[0] : e == 1 ? ps[1] : e == 2 ? ps[2] : ps[3];
-            const float vq = e == 0 ? pq[0] : e == 1 ? pq[1] : e == 2 ? pq[2] : pq[3];
-            s_sum[q * 256 + c0 + cc + e] += (double)vs;
-            s_sq[q * 256 + c0 + cc + e] += (double)vq;
-          }
+          for (int i = 0; i < 8; ++i) r4[i] = *reinterpret_cast<const float4*>(rb + i * rstep);
         }
+        long long tq3 = 0;
+        if (tprof) { tq3 = clock64(); tp_io += tq3 - tq2; }
+        if (p.ostats) {
+          // Column sums over the warp's 32 rows: lanes l, l^8, l^16, l^24 hold partials of the same four columns.  Recursive halving
+          // instead of a butterfly: in each round a lane keeps half of its columns and hands the other half to its partner, so 6
+          // shuffles do what 16 did and every lane ends with the total of ONE column (cc + 2*bit3 + bit4) - one owner per (row
+          // quadrant, channel), two FP64 adds per chunk with all lanes busy.  Same order of additions as the butterfly
+          // ((l + l^8) + (l^16 + l^24)): the sums are bit-identical.  The epilogue warps are issue- and MIO-latency bound (profile:
+          // ~900 cycles per chunk sat here), so the running sums' old values were requested before the shuffles.
+          const bool hi8 = (lane & 8) != 0, hi16 = (lane & 16) != 0;
+          const int sidx = q * 256 + c0 + cc + (hi8 ? 2 : 0) + (hi16 ? 1 : 0);
+          const double old_s = s_sum[sidx], old_q = s_sq[sidx];
+          float ks0 = hi8 ? ps[2] : ps[0], ks1 = hi8 ? ps[3] : ps[1], kq0 = hi8 ? pq[2] : pq[0], kq1 = hi8 ? pq[3] : pq[1];
+          ks0 += __shfl_xor_sync(0xffffffffu, hi8 ? ps[0] : ps[2], 8); ks1 += __shfl_xor_sync(0xffffffffu, hi8 ? ps[1] : ps[3], 8);
+          kq0 += __shfl_xor_sync(0xffffffffu, hi8 ? pq[0] : pq[2], 8); kq1 += __shfl_xor_sync(0xffffffffu, hi8 ? pq[1] : pq[3], 8);
+          float vs = hi16 ? ks1 : ks0, vq = hi16 ? kq1 : kq0;
+          vs += __shfl_xor_sync(0xffffffffu, hi16 ? ks0 : ks1, 16);
+          vq += __shfl_xor_sync(0xffffffffu, hi16 ? kq0 : kq1, 16);
+          s_sum[sidx] = old_s + (double)vs;
+          s_sq[sidx] = old_q + (double)vq;
+        }
+        if (tprof) tp_stats += clock64() - tq3;
       }
+      long long tf0 = 0;
+      if (tprof) tf0 = clock64();
       if (p.ostats) {
         // flush the per-CTA statistics when the (utterance, Cout tile) changes or the CTA is done
         bool flush = item + 1 >= item1;
@@ -730,9 +762,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_kernel(const UArgs u) {
           asm volatile("bar.sync 2, %0;" ::"n"(NEPI) : "memory");
         }
       }
+      if (tprof) tp_post += clock64() - tf0;
     }
     tc_fence_before();
-    if (u.prof && et == 0) { u.prof[blockIdx.x * 16 + 6] = clock64() - t_start; u.prof[blockIdx.x * 16 + 7] = tw_full; u.prof[blockIdx.x * 16 + 8] = item1 - item0; }
+    if (u.prof && et == 0) {
+      long long* pp = u.prof + blockIdx.x * 16;
+      pp[6] = clock64() - t_start; pp[7] = tw_full; pp[8] = item1 - item0;
+      pp[9] = tp_ld; pp[10] = tp_stage; pp[11] = tp_io; pp[12] = tp_stats; pp[13] = tp_pre; pp[14] = tp_top; pp[15] = tp_post;
+    }
   }
   __syncthreads();
   if (warp == NPW + 1) tmem_dealloc(tmem_base, (uint32_t)pl.tmem_cols);
@@ -802,7 +839,6 @@ __global__ void __launch_bounds__(256) pack_act_kernel(const ConvArgs p, int KS,
     uint4 o;
     if (WFMT == 2) {
       float hi[8], lo[8];
-#pragma unroll
       float satm = 0.f;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -988,7 +1024,7 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   if (dbg < 0) { const char* ev = getenv("TTSB_UMMA_DBG"); dbg = ev ? atoi(ev) : 0; }
   u.dbg = a.pro == PRO_ADAIN_SNAKE ? dbg : 0;
   static const int l2pf = getenv("TTSB_L2PF") ? atoi(getenv("TTSB_L2PF")) : 0;
-  u.l2pf = l2pf & 1;
+  u.l2pf = l2pf & 5;
   static int prof_on = -1;
   static long long* prof_buf = nullptr;
   if (prof_on < 0) {
@@ -1031,10 +1067,10 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
   if (prof_on) {      // diagnostic mode: synchronous, prints the mean cycle split of the roles for every launch
     static long long host[16 * 256];
     if (cudaStreamSynchronize(s) == cudaSuccess && cudaMemcpy(host, prof_buf, sizeof(long long) * 16 * grid, cudaMemcpyDeviceToHost) == cudaSuccess) {
-      double m[9] = {0};
+      double m[16] = {0};
       long long emax = 0, emin = 1LL << 62;
       for (int c = 0; c < grid; ++c) {
-        for (int i = 0; i < 9; ++i) m[i] += (double)host[c * 16 + i] / grid;
+        for (int i = 0; i < 16; ++i) m[i] += (double)host[c * 16 + i] / grid;
         emax = host[c * 16 + 6] > emax ? host[c * 16 + 6] : emax;
         emin = host[c * 16 + 6] < emin ? host[c * 16 + 6] : emin;
       }
@@ -1042,6 +1078,8 @@ cudaError_t launch_conv_umma(const ConvArgs& a, cudaStream_t s) {
       cudaEventElapsedTime(&us, pe0, pe1);
       fprintf(stderr, "umma pro=%d fmt=%d Cin=%d Cout=%d k=%d dil=%d grid=%d items/cta=%.1f | producer %.0f (wait %.0f) | mma %.0f (wait slab %.0f acc %.0f w %.0f) | epilogue %.0f (wait %.0f) cycles | epilogue min %lld max %lld | %.1f us\n",
               a.pro, a.wfmt, a.Cin, a.Cout, a.k, a.dil, grid, m[8], m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], emin, emax, us * 1000.f);
+      fprintf(stderr, "   epilogue phases per item (cycles): tmem ld %.0f | staging %.0f | global io + math %.0f | statistics %.0f | item prelude %.0f | chunk top %.0f | flush %.0f | res=%d acc=%d stats=%d\n", m[9] / m[8],
+              m[10] / m[8], m[11] / m[8], m[12] / m[8], m[13] / m[8], m[14] / m[8], m[15] / m[8], a.res != nullptr, a.accumulate, a.ostats != nullptr);
     }
   }
   return launched();

@@ -168,6 +168,28 @@ struct Loader {
     pack_conv(w, b ? &b->data : nullptr, c, want);
     return true;
   }
+  // Conv1d whose channel counts are padded with zero weights / zero bias up to (cout_to, cin_to).  For the two 22-channel layers of
+  // the generator (conv_post 128 -> 22, noise_convs[1] 22 -> 128): both buffers already have 24 floats per row with the last two
+  // zero, and 22 is not a multiple of 4 (8), which sent the epilogue (the producers) of the tensor-core kernel down its scalar
+  // ragged-channel path - 8.5 k cycles per tile instead of 1.2 k (TTSB_UMMA_PROF).  The extra output columns are exact zeros.
+  bool conv_padded(const std::string& prefix, ConvW& c, int cout_to, int cin_to, int want) {
+    HostTensor w;
+    if (!weight(prefix, w)) return false;
+    const HostTensor* b = get(prefix + ".bias");
+    if (!b) return false;
+    const int Co = (int)w.shape[0], Ci = (int)w.shape[1], k = w.shape.size() > 2 ? (int)w.shape[2] : 1;
+    const int Co2 = std::max(Co, cout_to), Ci2 = std::max(Ci, cin_to);
+    HostTensor wp;
+    wp.shape = {Co2, Ci2, k};
+    wp.data.assign((size_t)Co2 * Ci2 * k, 0.f);
+    for (int co = 0; co < Co; ++co)
+      for (int ci = 0; ci < Ci; ++ci)
+        for (int j = 0; j < k; ++j) wp.data[((size_t)co * Ci2 + ci) * k + j] = w.data[((size_t)co * Ci + ci) * k + j];
+    std::vector<float> bp((size_t)Co2, 0.f);
+    for (int co = 0; co < Co && co < (int)b->data.size(); ++co) bp[co] = b->data[co];
+    pack_conv(wp, &bp, c, want);
+    return true;
+  }
   bool lstm(const std::string& prefix, LstmW& l);
   bool resblk1d(const std::string& prefix, ResBlk1dW& r, int cin, int cout, bool up, std::vector<float>& style_w, std::vector<float>& style_b,
                 int want);
@@ -354,7 +376,7 @@ int engine_finalize(Engine& e) {
   const std::string G = "decoder.generator.";
   e.src_lin_w = ld.upload_named(G + "m_source.l_linear.weight");
   e.src_lin_b = ld.upload_named(G + "m_source.l_linear.bias");
-  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, 0) && ld.conv(G + "noise_convs.1", e.noise_conv[1], true, 3);
+  ok = ok && ld.conv(G + "noise_convs.0", e.noise_conv[0], true, 0) && ld.conv_padded(G + "noise_convs.1", e.noise_conv[1], 0, 24, 3);
   if (ok) {
     // noise_convs[0]: Conv1d(22, 256, k12, stride 6, pad 3) over STFT frames == k3/pad1 conv over frames regrouped six at a time
     // ([blocks, 6 x 24] view of the channels-last har buffer): tap in {0,1,2}, slot i in 0..5  <->  original tap j = 6 tap + i - 3
@@ -377,7 +399,7 @@ int engine_finalize(Engine& e) {
   ok = ok && ld.resblock1(G + "noise_res.0", e.noise_res[0], 256, 7, swD, sbD) && ld.resblock1(G + "noise_res.1", e.noise_res[1], 128, 11, swD, sbD);
   const int rk[3] = {3, 7, 11};
   for (int i = 0; i < 6 && ok; ++i) ok = ok && ld.resblock1(G + "resblocks." + std::to_string(i), e.resblk[i], i < 3 ? 256 : 128, rk[i % 3], swD, sbD);
-  ok = ok && ld.conv(G + "conv_post", e.conv_post, true, 3);
+  ok = ok && ld.conv_padded(G + "conv_post", e.conv_post, 24, 0, 3);
   if (ok) {
     HostTensor w;
     w.shape = {(int64_t)sbP.size(), 128}; w.data = swP; ld.pack_conv(w, &sbP, e.style_pred, 0);
