@@ -174,6 +174,7 @@ __device__ __forceinline__ void adain_coef(const double* st, int n, float gamma,
 namespace ttsb {
 // host: repack fp32 [k][Cin][ldw] weights into the bf16 shared-memory image the tcgen05 kernel streams (conv_umma.cu)
 // split_scale (fmt 2 only): receives the per-layer power-of-two weight scale (ConvArgs::split_wscale)
+void pack_umma_wa_weights(const float* w, int k, int C, int ldw, int fmt, std::vector<uint16_t>& out);      // conv_umma_wa.cu
 void pack_umma_weights(const float* w, int k, int Cin, int Cout, int ldw, int fmt, std::vector<uint16_t>& out, int& cin_pad, int& cout_pad,
                        float* split_scale = nullptr);
 const char* last_error();

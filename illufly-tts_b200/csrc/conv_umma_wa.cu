@@ -22,6 +22,16 @@
 // fed by the bulk-copy engine, an mbarrier ring of weight stages, two TMEM accumulators (2 x 256 columns = all of TMEM).
 // Operand layouts: no-swizzle K-major [8-channel plane][row][16 B] for both; a tap is a row offset of the B descriptor.
 // Fused prologue: InstanceNorm normalise + AdaIN affine + Snake (PRO_ADAIN_SNAKE), as conv_umma.cu.
+//
+// 256-channel layers (stage 0 of the generator; NH = 2).  The same roles work in UNITS of 128 channels: a slab holds one 128-channel
+// half h of the tile's input rows, an accumulator one 128-channel half mt of its outputs.  Per tile the MMA warp runs
+//     for h: for mt: for tap: D[mt] += W[tap][mt half, h half] X[h half]^T
+// so a slab is released after half of the tile's MMAs (the producers stay one unit ahead, as with 128 channels) and the two
+// accumulators - all 512 TMEM columns - are staggered: D[0] completes one (unit, mt) pass before D[1], the epilogue drains D[0]
+// under the MMAs of D[1] and D[1] under the next tile's first pass.  Units and accumulations are numbered uc = n NH + h and
+// g = n NH + mt; their barrier slot is the number's low bit and the phase the next bit - for NH = 1 exactly the two-slot scheme above.
+// The weights come in pack order [h][mt][tap][64-channel chunk] (pack_umma_wa_weights), 16 KB per stage as before; the raw-row ring
+// takes the unit's 128 channels of each row (one bulk copy per row, the lanes of the row loader side by side).
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
@@ -29,6 +39,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 namespace ttsb {
 
@@ -52,6 +63,7 @@ struct WPlan {
   int SR;                               // slab rows: TN + (k-1) dil, made odd (conflict-free 16-B stores across planes)
   int nstage, nraw, rps, rch, nch;      // weight stages; ring slots, rows per producer thread per slot, rows per slot, slots per slab
   int items, per_cta;
+  int nh;                               // 128-channel halves: 1 (128-channel layers) or 2 (256)
   uint32_t off_bar, off_par, off_slab, slab_bytes, off_raw, raw_bytes, off_w, smem_bytes, row_bytes;
 };
 
@@ -59,7 +71,6 @@ struct WArgs {
   ConvArgs a;
   WPlan p;
   long long* prof;
-  int l2pf;            // row loader asks the L2 for the next tile's rows (TTSB_L2PF bit 1; default off: measured slower, the prefetch doubles the request traffic of a throughput-bound memory system)
 };
 
 // The epilogue of one tile for one warp: 128 time steps of this thread's output channel.
@@ -70,12 +81,12 @@ struct WArgs {
 // FULL: the half tile lies inside the utterance - straight-line code; otherwise rows past the utterance's end are predicated.
 //   y = (acc + bias [+ res]) [* os] [+ y_old]; dsum / dsq += this thread's sum / sum of squares of what it stored
 // RES: 0 = no residual, 1 = fp32 residual rows, 2 = fp16 residual rows (the block's running value between its iterations)
-template <int RES, bool SCALE, bool ACC, bool YH, bool FULL>
+template <int RES, bool SCALE, bool ACC, bool YH, bool FULL, int LD>
 __device__ __forceinline__ void epi_tile(const uint32_t tacc, const int nv, const float bias, const float os, float* __restrict__ yb, __half* __restrict__ yh,
                                          const void* __restrict__ rbv, const uint32_t bar_empty, const int lane, double& dsum, double& dsq) {
   const float* __restrict__ rb = reinterpret_cast<const float*>(rbv);
   const __half* __restrict__ rh = reinterpret_cast<const __half*>(rbv);
-  constexpr size_t ldy = CH, ldr = CH;             // rows of y and res are whole channel rows (conv_umma_wa_supported): the row offsets
+  constexpr size_t ldy = LD, ldr = LD;             // rows of y and res are whole channel rows (conv_umma_wa_supported): the row offsets
                                                    // below are immediates of the load / store instructions, not address registers
   constexpr int W = ACC ? 16 : 32;                 // window depth per stream (two streams when the old output is read too)
   float rw[W], yw[ACC ? W : 1];
@@ -122,15 +133,16 @@ __device__ __forceinline__ void epi_tile(const uint32_t tacc, const int nv, cons
   }
 }
 
-template <int RES, bool SCALE, bool ACC, bool YH>
+template <int RES, bool SCALE, bool ACC, bool YH, int LD>
 __device__ __forceinline__ void epi_tile_any(const uint32_t tacc, const int nv, const float bias, const float os, float* yb, __half* yh, const void* rb,
                                              const uint32_t bar_empty, const int lane, double& dsum, double& dsq) {
-  if (nv >= 128) epi_tile<RES, SCALE, ACC, YH, true>(tacc, 128, bias, os, yb, yh, rb, bar_empty, lane, dsum, dsq);
-  else epi_tile<RES, SCALE, ACC, YH, false>(tacc, nv, bias, os, yb, yh, rb, bar_empty, lane, dsum, dsq);
+  if (nv >= 128) epi_tile<RES, SCALE, ACC, YH, true, LD>(tacc, 128, bias, os, yb, yh, rb, bar_empty, lane, dsum, dsq);
+  else epi_tile<RES, SCALE, ACC, YH, false, LD>(tacc, nv, bias, os, yb, yh, rb, bar_empty, lane, dsum, dsq);
 }
 
-template <int WFMT, bool XH, bool YH>
+template <int WFMT, bool XH, bool YH, int NH>
 __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u) {
+  constexpr int CT = NH * CH;                      // channels of the layer (Cin = Cout)
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& p = u.a;
   const WPlan& pl = u.p;
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
   auto bar_acc_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 6 + b); };
   auto bar_raw_full = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 8 + b); };
   auto bar_raw_empty = [&](int b) { return bar0 + 8u * (2 * MAXSTAGE + 8 + MAXRAW + b); };
-  float* s_par = reinterpret_cast<float*>(smem + pl.off_par);       // [5][CH]: A, B (+k), 2 alpha A, 2 alpha B, k
+  float* s_par = reinterpret_cast<float*>(smem + pl.off_par);       // [5][CT]: A, B (+k), 2 alpha A, 2 alpha B, k
 
   const int item0 = blockIdx.x * pl.per_cta;
   const int item1 = min(item0 + pl.per_cta, pl.items);
@@ -204,10 +216,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     for (int item = item0; item < item1; ++item, ++n) {
       const Tile tile = p.tiles[item];
       const Seg seg = p.segs[tile.seg];
-      if (tile.seg != cur_seg) {
+      const bool new_seg = tile.seg != cur_seg;
+      if (new_seg) {
         // per-(utterance, channel) AdaIN coefficients; only producers read them, so a producer-only barrier suffices
         asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
-        if (tid < CH) {
+        if (tid < CT) {
           const int c = tid;
           float mean, a, b;
           const double* st = p.pstats + ((size_t)tile.seg * p.ld_pstats + c) * 2;
@@ -217,77 +230,84 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
           // (w + k) - k cos(2 alpha w),  k = 1/(2 alpha):  wk = x A + (B + k),  t = x (2 alpha A) + 2 alpha B
           const float Bf = fmaf(-mean, a, b);
           const float kk = 0.5f / al;
-          s_par[c] = a; s_par[CH + c] = Bf + kk; s_par[2 * CH + c] = 2.f * al * a; s_par[3 * CH + c] = 2.f * al * Bf; s_par[4 * CH + c] = kk;
+          s_par[c] = a; s_par[CT + c] = Bf + kk; s_par[2 * CT + c] = 2.f * al * a; s_par[3 * CT + c] = 2.f * al * Bf; s_par[4 * CT + c] = kk;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          pA[e] = s_par[c0 + e]; pB[e] = s_par[CH + c0 + e]; pA2[e] = s_par[2 * CH + c0 + e]; pB2[e] = s_par[3 * CH + c0 + e]; pK[e] = s_par[4 * CH + c0 + e];
-        }
         cur_seg = tile.seg;
       }
-      const uint32_t b = n & 1u;
-      mbar_wait_t(bar_slab_empty(b), ((n >> 1) & 1u) ^ 1u, t_wait);
-      uint8_t* slab = smem + pl.off_slab + (size_t)b * pl.slab_bytes + (size_t)pln * SR * 16;
       const int row_lo = tile.t0 - p.pad;
-      if (pl.nraw > 0 && row_lo >= 0 && row_lo + SR <= seg.in_len) {
-        // interior tile: the row loader streams the raw rows through the ring with the bulk-copy engine
-        for (int ch = 0; ch < pl.nch; ++ch) {
-          mbar_wait_t(bar_raw_full(rslot), rphase, t_wait);
-          const uint8_t* slot = smem + pl.off_raw + (size_t)rslot * pl.raw_bytes;
-          const int ra = ch * pl.rch + r0, rb = ra + RPP;
-          const bool hasa = ra < SR, hasb = pl.rps > 1 && rb < SR;
-          float va[8], vb[8];
-          if (XH) {
-            const uint4 qa = *reinterpret_cast<const uint4*>(slot + (size_t)(r0 * CH + c0) * 2);
-            const uint4 qb = *reinterpret_cast<const uint4*>(slot + (size_t)((hasb ? r0 + RPP : r0) * CH + c0) * 2);
-            unpack_h8(qa, va); unpack_h8(qb, vb);
-          } else {
-            // groups of four lanes alternate which 16-B half of their 32 B they read first: eight lanes x 16 B at a 32-B
-            // stride would hit every bank group twice
-            const int hf = (tid >> 2) & 1;
-            const float* sa = reinterpret_cast<const float*>(slot) + r0 * CH + c0;
-            const float* sb = hasb ? sa + RPP * CH : sa;
-            const float4 ax = *reinterpret_cast<const float4*>(sa + 4 * hf), ay = *reinterpret_cast<const float4*>(sa + 4 * (hf ^ 1));
-            const float4 bx = *reinterpret_cast<const float4*>(sb + 4 * hf), by = *reinterpret_cast<const float4*>(sb + 4 * (hf ^ 1));
-            const float4 a0 = hf ? ay : ax, a1 = hf ? ax : ay, b0 = hf ? by : bx, b1 = hf ? bx : by;
-            va[0] = a0.x; va[1] = a0.y; va[2] = a0.z; va[3] = a0.w; va[4] = a1.x; va[5] = a1.y; va[6] = a1.z; va[7] = a1.w;
-            vb[0] = b0.x; vb[1] = b0.y; vb[2] = b0.z; vb[3] = b0.w; vb[4] = b1.x; vb[5] = b1.y; vb[6] = b1.z; vb[7] = b1.w;
+#pragma unroll 1
+      for (int h = 0; h < NH; ++h) {
+        const int cg = h * CH + c0;                 // this thread's eight channels of the layer
+        if (NH > 1 || new_seg) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            pA[e] = s_par[cg + e]; pB[e] = s_par[CT + cg + e]; pA2[e] = s_par[2 * CT + cg + e]; pB2[e] = s_par[3 * CT + cg + e]; pK[e] = s_par[4 * CT + cg + e];
           }
-          if (hasa) xform_store(slab, ra, va);
-          if (hasb) xform_store(slab, rb, vb);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_raw_empty(rslot));      // this warp is done reading the slot
-          if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
         }
-      } else {
-        // edge tile of an utterance (or no ring): rows outside the utterance are zero AFTER the activation, as torch pads
-        for (int rr = r0; rr < SR; rr += RPP) {
-          const int tin = row_lo + rr;
-          float v[8];
-          if (tin >= 0 && tin < seg.in_len) {
-            const uint8_t* src = xbytes + ((size_t)(seg.in_off + tin) * p.ldx + c0) * ESZ;
-            if (XH) unpack_h8(__ldg(reinterpret_cast<const uint4*>(src)), v);
-            else {
-              const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-              v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        const uint32_t uc = n * NH + h;             // unit number: slab slot = low bit, phase = next bit
+        const uint32_t b = uc & 1u;
+        mbar_wait_t(bar_slab_empty(b), ((uc >> 1) & 1u) ^ 1u, t_wait);
+        uint8_t* slab = smem + pl.off_slab + (size_t)b * pl.slab_bytes + (size_t)pln * SR * 16;
+        if (pl.nraw > 0 && row_lo >= 0 && row_lo + SR <= seg.in_len) {
+          // interior tile: the row loader streams the unit's raw rows (128 channels each) through the ring with the bulk-copy engine
+          for (int ch = 0; ch < pl.nch; ++ch) {
+            mbar_wait_t(bar_raw_full(rslot), rphase, t_wait);
+            const uint8_t* slot = smem + pl.off_raw + (size_t)rslot * pl.raw_bytes;
+            const int ra = ch * pl.rch + r0, rb = ra + RPP;
+            const bool hasa = ra < SR, hasb = pl.rps > 1 && rb < SR;
+            float va[8], vb[8];
+            if (XH) {
+              const uint4 qa = *reinterpret_cast<const uint4*>(slot + (size_t)(r0 * CH + c0) * 2);
+              const uint4 qb = *reinterpret_cast<const uint4*>(slot + (size_t)((hasb ? r0 + RPP : r0) * CH + c0) * 2);
+              unpack_h8(qa, va); unpack_h8(qb, vb);
+            } else {
+              // groups of four lanes alternate which 16-B half of their 32 B they read first: eight lanes x 16 B at a 32-B
+              // stride would hit every bank group twice
+              const int hf = (tid >> 2) & 1;
+              const float* sa = reinterpret_cast<const float*>(slot) + r0 * CH + c0;
+              const float* sb = hasb ? sa + RPP * CH : sa;
+              const float4 ax = *reinterpret_cast<const float4*>(sa + 4 * hf), ay = *reinterpret_cast<const float4*>(sa + 4 * (hf ^ 1));
+              const float4 bx = *reinterpret_cast<const float4*>(sb + 4 * hf), by = *reinterpret_cast<const float4*>(sb + 4 * (hf ^ 1));
+              const float4 a0 = hf ? ay : ax, a1 = hf ? ax : ay, b0 = hf ? by : bx, b1 = hf ? bx : by;
+              va[0] = a0.x; va[1] = a0.y; va[2] = a0.z; va[3] = a0.w; va[4] = a1.x; va[5] = a1.y; va[6] = a1.z; va[7] = a1.w;
+              vb[0] = b0.x; vb[1] = b0.y; vb[2] = b0.z; vb[3] = b0.w; vb[4] = b1.x; vb[5] = b1.y; vb[6] = b1.z; vb[7] = b1.w;
             }
-            xform_store(slab, rr, v);
-          } else {
-            *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = make_uint4(0u, 0u, 0u, 0u);
+            if (hasa) xform_store(slab, ra, va);
+            if (hasb) xform_store(slab, rb, vb);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_raw_empty(rslot));      // this warp is done reading the slot
+            if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
+          }
+        } else {
+          // edge tile of an utterance (or no ring): rows outside the utterance are zero AFTER the activation, as torch pads
+          for (int rr = r0; rr < SR; rr += RPP) {
+            const int tin = row_lo + rr;
+            float v[8];
+            if (tin >= 0 && tin < seg.in_len) {
+              const uint8_t* src = xbytes + ((size_t)(seg.in_off + tin) * p.ldx + cg) * ESZ;
+              if (XH) unpack_h8(__ldg(reinterpret_cast<const uint4*>(src)), v);
+              else {
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(src)), q1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+              }
+              xform_store(slab, rr, v);
+            } else {
+              *reinterpret_cast<uint4*>(slab + (size_t)rr * 16) = make_uint4(0u, 0u, 0u, 0u);
+            }
           }
         }
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_slab_full(b));
       }
-      fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_slab_full(b));
     }
     if (u.prof && tid == 0) { u.prof[blockIdx.x * 16 + 0] = clock64() - t_start; u.prof[blockIdx.x * 16 + 1] = t_wait; }
   } else if (warp == 8) {
     // =================== weight loader (bulk-copy engine) ===================
     if (lane == 0) {
       uint32_t it = 0;
-      const int nblk = p.k * (CH / KCH);                 // stages per tile, in pack order [tap][64-channel chunk]
+      const int nblk = NH * NH * p.k * (CH / KCH);       // stages per tile, in pack order [h][mt][tap][64-channel chunk]
       for (int item = item0; item < item1; ++item)
         for (int blk = 0; blk < nblk; ++blk, ++it) {
           const uint32_t s = it % NS;
@@ -313,32 +333,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     long long tw_slab = 0, tw_acc = 0, tw_w = 0;
     const long long t_start = clock64();
     for (int item = item0; item < item1; ++item, ++n) {
-      const uint32_t slot = n & 1u;
-      mbar_wait_t(bar_acc_empty(slot), ((n >> 1) & 1u) ^ 1u, tw_acc);       // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t tacc = tmem_u + slot * (uint32_t)TN;
-      mbar_wait_t(bar_slab_full(slot), (n >> 1) & 1u, tw_slab);
-      tc_fence_after();
-      const uint32_t sbase = slab0 + slot * pl.slab_bytes;
-      uint32_t first = 1;
-      for (int j = 0; j < p.k; ++j)
-        for (int kc = 0; kc < CH / KCH; ++kc, ++it) {
-          const uint32_t s = it % NS;
-          mbar_wait_t(bar_full(s), (it / NS) & 1u, tw_w);
-          tc_fence_after();
-          const uint64_t ad0 = a_desc0 + (uint64_t)((w0 + s * WSTAGE_BYTES) >> 4);
-          const uint64_t bd0 = b_desc0 + (uint64_t)((sbase >> 4) + (uint32_t)(kc * 8 * SR + j * p.dil));
-#pragma unroll
-          for (int kk = 0; kk < KCH / 16; ++kk) {
-            if (leader) umma_bf16(tacc, ad0 + (uint64_t)(kk * a_kstep), bd0 + (uint64_t)(kk * b_kstep), idesc, first ? 0u : 1u);
-            first = 0;
+#pragma unroll 1
+      for (int h = 0; h < NH; ++h) {
+        const uint32_t uc = n * NH + h;                  // unit: one 128-channel half of the tile's input rows
+        const uint32_t sl = uc & 1u;
+        mbar_wait_t(bar_slab_full(sl), (uc >> 1) & 1u, tw_slab);
+        tc_fence_after();
+        const uint32_t sbase = slab0 + sl * pl.slab_bytes;
+#pragma unroll 1
+        for (int mt = 0; mt < NH; ++mt) {
+          const uint32_t g = n * NH + mt;                // accumulation: one 128-channel half of the tile's outputs
+          const uint32_t slot = g & 1u;
+          if (h == 0) {
+            mbar_wait_t(bar_acc_empty(slot), ((g >> 1) & 1u) ^ 1u, tw_acc);       // epilogue has drained this accumulator
+            tc_fence_after();
           }
-          if (leader) umma_commit(bar_empty(s));            // weight stage free once these MMAs have read it
-          __syncwarp();
+          const uint32_t tacc = tmem_u + slot * (uint32_t)TN;
+          uint32_t first = h == 0 ? 1u : 0u;
+          for (int j = 0; j < p.k; ++j)
+            for (int kc = 0; kc < CH / KCH; ++kc, ++it) {
+              const uint32_t s = it % NS;
+              mbar_wait_t(bar_full(s), (it / NS) & 1u, tw_w);
+              tc_fence_after();
+              const uint64_t ad0 = a_desc0 + (uint64_t)((w0 + s * WSTAGE_BYTES) >> 4);
+              const uint64_t bd0 = b_desc0 + (uint64_t)((sbase >> 4) + (uint32_t)(kc * 8 * SR + j * p.dil));
+#pragma unroll
+              for (int kk = 0; kk < KCH / 16; ++kk) {
+                if (leader) umma_bf16(tacc, ad0 + (uint64_t)(kk * a_kstep), bd0 + (uint64_t)(kk * b_kstep), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              if (leader) umma_commit(bar_empty(s));            // weight stage free once these MMAs have read it
+              __syncwarp();
+            }
+          if (h == NH - 1) {
+            if (leader) umma_commit(bar_acc_full(slot));        // this half of the tile's outputs is complete
+            __syncwarp();
+          }
         }
-      if (leader) umma_commit(bar_slab_empty(slot));        // slab free once every MMA issued so far has completed
-      if (leader) umma_commit(bar_acc_full(slot));          // accumulator of this item complete
-      __syncwarp();
+        if (leader) umma_commit(bar_slab_empty(sl));            // slab free once every MMA issued so far has completed
+        __syncwarp();
+      }
     }
     if (u.prof && lane == 0) {
       long long* pp = u.prof + blockIdx.x * 16;
@@ -346,104 +380,98 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     }
   } else if (warp == 18) {
     // =================== row loader: raw activation rows -> ring (bulk-copy engine) ===================
-    if (lane == 0) {
-      uint32_t rslot = 0, rphase = 0;
-      // The ring holds 32 KB: at HBM latency that is ~20 GB/s per SM, less than a tile needs.  One tile ahead, the loader asks the
-      // L2 for the rows the ring (and the epilogue's residual loads) will want next, so that those requests are L2 hits.
-      auto prefetch_tile = [&](int item) {
-        if (item >= item1 || !u.l2pf) return;
-        const Tile tl = p.tiles[item];
-        const Seg sg = p.segs[tl.seg];
-        int lo = tl.t0 - p.pad, hi = lo + SR;
-        lo = max(lo, 0); hi = min(hi, sg.in_len);
-        if (hi > lo) {
-          const uint8_t* src = xbytes + (size_t)(sg.in_off + lo) * pl.row_bytes;
-          const uint32_t bytes = (uint32_t)(hi - lo) * pl.row_bytes;
-          for (uint32_t o = 0; o < bytes; o += 16384u) prefetch_l2(src + o, min(16384u, bytes - o));
-        }
-        if (p.res) {
-          const int nr = min(TN, sg.out_len - tl.t0);
-          const uint32_t rsz = p.r_f16 ? 2u : 4u;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.res) + (size_t)(sg.out_off + tl.t0) * p.ldr * rsz;
-          const uint32_t bytes = (uint32_t)nr * (uint32_t)p.ldr * rsz;
-          for (uint32_t o = 0; o < bytes; o += 16384u) prefetch_l2(src + o, min(16384u, bytes - o));
-        }
-        if (p.accumulate && !YH) {                    // the running sum of the three parallel resblocks is read back too
-          const int nr = min(TN, sg.out_len - tl.t0);
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.y + (size_t)(sg.out_off + tl.t0) * p.ldy);
-          const uint32_t bytes = (uint32_t)nr * (uint32_t)p.ldy * 4u;
-          for (uint32_t o = 0; o < bytes; o += 16384u) prefetch_l2(src + o, min(16384u, bytes - o));
-        }
-      };
-      prefetch_tile(item0);
-      for (int item = item0; item < item1; ++item) {
-        prefetch_tile(item + 1);
-        if (pl.nraw == 0) continue;
-        const Tile tile = p.tiles[item];
-        const Seg seg = p.segs[tile.seg];
-        const int row_lo = tile.t0 - p.pad;
-        if (!(row_lo >= 0 && row_lo + SR <= seg.in_len)) continue;      // edge tile: the producers load it themselves
+    // (An L2 prefetch of the next tile's rows from here was measured slower - it doubles the request traffic of a memory system that
+    //  is throughput-bound under this kernel - and was removed; profiles/r02_bench_log.md, row 7.)
+    uint32_t rslot = 0, rphase = 0;
+    const uint32_t ubytes = (uint32_t)CH * ESZ;              // a unit's share of one row
+    for (int item = item0; item < item1; ++item) {
+      if (pl.nraw == 0) continue;
+      const Tile tile = p.tiles[item];
+      const Seg seg = p.segs[tile.seg];
+      const int row_lo = tile.t0 - p.pad;
+      if (!(row_lo >= 0 && row_lo + SR <= seg.in_len)) continue;      // edge tile: the producers load it themselves
+#pragma unroll 1
+      for (int h = 0; h < NH; ++h)
         for (int ch = 0; ch < pl.nch; ++ch) {
-          mbar_wait(bar_raw_empty(rslot), rphase ^ 1u);
+          if (lane == 0) mbar_wait(bar_raw_empty(rslot), rphase ^ 1u);
+          __syncwarp();
           const int rows_n = min(pl.rch, SR - ch * pl.rch);
-          const uint8_t* src = xbytes + (size_t)(seg.in_off + row_lo + ch * pl.rch) * pl.row_bytes;      // ldx == CH: rows are contiguous
-          const uint32_t bytes = (uint32_t)rows_n * pl.row_bytes;
-          mbar_expect_tx(bar_raw_full(rslot), bytes);
-          bulk_g2s(smem_u32(smem + pl.off_raw + (size_t)rslot * pl.raw_bytes), src, bytes, bar_raw_full(rslot));
+          const uint8_t* src = xbytes + ((size_t)(seg.in_off + row_lo + ch * pl.rch) * CT + (size_t)h * CH) * ESZ;
+          const uint32_t dst = smem_u32(smem + pl.off_raw + (size_t)rslot * pl.raw_bytes);
+          if (lane == 0) mbar_expect_tx(bar_raw_full(rslot), (uint32_t)rows_n * ubytes);
+          __syncwarp();                                    // the byte count is registered before any copy can complete
+          if (NH == 1) {                                   // ldx == CH: the rows are one contiguous block
+            if (lane == 0) bulk_g2s(dst, src, (uint32_t)rows_n * ubytes, bar_raw_full(rslot));
+          } else {                                         // 128 of a row's 256 channels: one copy per row, the lanes side by side (rch <= 32)
+            if (lane < rows_n) bulk_g2s(dst + (uint32_t)lane * ubytes, src + (size_t)lane * CT * ESZ, ubytes, bar_raw_full(rslot));
+          }
           if (++rslot == (uint32_t)pl.nraw) { rslot = 0; rphase ^= 1u; }
         }
-      }
     }
   } else {
     // =================== epilogue: 8 warps, TMEM lane quadrant q = warp % 4, columns [128 half, 128 half + 128) ===================
     const int q = warp & 3;
     const int half = (warp - 10) >> 2;
-    const int c = q * 32 + lane;                       // this thread's output channel
-    const float bias = p.bias ? p.bias[c] : 0.f;
+    const int cl = q * 32 + lane;                      // this thread's output channel within a 128-channel half
+    // per-thread state of the (up to) two output halves in scalars, selected by mt: the loop over mt stays rolled (one copy of the
+    // nine epilogue variants) and nothing lives in local memory
+    const float bias0 = p.bias ? p.bias[cl] : 0.f, bias1 = (p.bias && NH > 1) ? p.bias[CH + cl] : 0.f;
+    double dsum0 = 0.0, dsq0 = 0.0, dsum1 = 0.0, dsq1 = 0.0;
     const bool has_res = p.res != nullptr, acc = p.accumulate != 0, sc = p.out_scale != 1.0f;
-    constexpr size_t ldy = CH, ldr = CH;
-    double dsum = 0.0, dsq = 0.0;
+    constexpr size_t ldy = CT, ldr = CT;
     uint32_t n = 0;
     long long tw_full = 0;
     const long long t_start = clock64();
     for (int item = item0; item < item1; ++item, ++n) {
       const Tile tile = p.tiles[item];
       const Seg seg = p.segs[tile.seg];
-      const uint32_t slot = n & 1u;
-      mbar_wait_t(bar_acc_full(slot), (n >> 1) & 1u, tw_full);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + slot * (uint32_t)TN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
       const int tbase = tile.t0 + half * 128;
       const int nv = seg.out_len - tbase;              // rows of this half tile inside the utterance (<= 0: nothing to store)
       const size_t row0 = (size_t)(seg.out_off + tbase);
-      float* yb = YH ? nullptr : p.y + row0 * ldy + c;
-      __half* yh = YH ? reinterpret_cast<__half*>(p.y) + row0 * ldy + c : nullptr;
-      // residual rows: fp32 (the stage's input, first iteration of a block) or fp16 (the block's running value)
-      const void* rb = !has_res ? nullptr
-                       : p.r_f16 ? static_cast<const void*>(reinterpret_cast<const __half*>(p.res) + row0 * ldr + c)
-                                 : static_cast<const void*>(p.res + row0 * ldr + c);
-      const uint32_t be = bar_acc_empty(slot);
-      if (YH) {                        // c1 (no residual) and the c2 of a block's first two iterations (running value out as fp16)
-        if (!has_res) epi_tile_any<0, false, false, true>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
-        else if (p.r_f16) epi_tile_any<2, false, false, true>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
-        else epi_tile_any<1, false, false, true>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
-      } else if (p.r_f16) {            // the c2 of a block's last iteration: fp32 out (scaled, accumulated over the parallel blocks)
-        if (acc) epi_tile_any<2, true, true, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
-        else if (sc) epi_tile_any<2, true, false, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
-        else epi_tile_any<2, false, false, false>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
-      } else {
-        if (acc) epi_tile_any<1, true, true, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
-        else if (sc) epi_tile_any<1, true, false, false>(tacc, nv, bias, p.out_scale, yb, yh, rb, be, lane, dsum, dsq);
-        else epi_tile_any<1, false, false, false>(tacc, nv, bias, 1.f, yb, yh, rb, be, lane, dsum, dsq);
+#pragma unroll 1
+      for (int mt = 0; mt < NH; ++mt) {
+        const uint32_t g = n * NH + mt;                // accumulation number: slot = low bit, phase = next bit
+        const uint32_t slot = g & 1u;
+        const int c = mt * CH + cl;
+        const float bs = mt ? bias1 : bias0;
+        double ds = mt ? dsum1 : dsum0, dq = mt ? dsq1 : dsq0;
+        mbar_wait_t(bar_acc_full(slot), (g >> 1) & 1u, tw_full);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + slot * (uint32_t)TN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+        float* yb = YH ? nullptr : p.y + row0 * ldy + c;
+        __half* yh = YH ? reinterpret_cast<__half*>(p.y) + row0 * ldy + c : nullptr;
+        // residual rows: fp32 (the stage's input, first iteration of a block) or fp16 (the block's running value)
+        const void* rb = !has_res ? nullptr
+                         : p.r_f16 ? static_cast<const void*>(reinterpret_cast<const __half*>(p.res) + row0 * ldr + c)
+                                   : static_cast<const void*>(p.res + row0 * ldr + c);
+        const uint32_t be = bar_acc_empty(slot);
+        if (YH) {                        // c1 (no residual) and the c2 of a block's first two iterations (running value out as fp16)
+          if (!has_res) epi_tile_any<0, false, false, true, CT>(tacc, nv, bs, 1.f, yb, yh, rb, be, lane, ds, dq);
+          else if (p.r_f16) epi_tile_any<2, false, false, true, CT>(tacc, nv, bs, 1.f, yb, yh, rb, be, lane, ds, dq);
+          else epi_tile_any<1, false, false, true, CT>(tacc, nv, bs, 1.f, yb, yh, rb, be, lane, ds, dq);
+        } else if (p.r_f16) {            // the c2 of a block's last iteration: fp32 out (scaled, accumulated over the parallel blocks)
+          if (acc) epi_tile_any<2, true, true, false, CT>(tacc, nv, bs, p.out_scale, yb, yh, rb, be, lane, ds, dq);
+          else if (sc) epi_tile_any<2, true, false, false, CT>(tacc, nv, bs, p.out_scale, yb, yh, rb, be, lane, ds, dq);
+          else epi_tile_any<2, false, false, false, CT>(tacc, nv, bs, 1.f, yb, yh, rb, be, lane, ds, dq);
+        } else {
+          if (acc) epi_tile_any<1, true, true, false, CT>(tacc, nv, bs, p.out_scale, yb, yh, rb, be, lane, ds, dq);
+          else if (sc) epi_tile_any<1, true, false, false, CT>(tacc, nv, bs, p.out_scale, yb, yh, rb, be, lane, ds, dq);
+          else epi_tile_any<1, false, false, false, CT>(tacc, nv, bs, 1.f, yb, yh, rb, be, lane, ds, dq);
+        }
+        if (mt) { dsum1 = ds; dsq1 = dq; } else { dsum0 = ds; dsq0 = dq; }
       }
       if (p.ostats) {
         // flush this thread's running sums when the utterance changes or the CTA is done
         const bool flush = item + 1 >= item1 || p.tiles[item + 1].seg != tile.seg;
         if (flush) {
-          double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + c) * 2;
-          atomicAdd(st, dsum);
-          atomicAdd(st + 1, dsq);
-          dsum = 0.0; dsq = 0.0;
+          double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + cl) * 2;
+          atomicAdd(st, dsum0);
+          atomicAdd(st + 1, dsq0);
+          if (NH > 1) {
+            atomicAdd(st + 2 * CH, dsum1);
+            atomicAdd(st + 2 * CH + 1, dsq1);
+          }
+          dsum0 = 0.0; dsq0 = 0.0; dsum1 = 0.0; dsq1 = 0.0;
         }
       }
     }
@@ -455,13 +483,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
 }
 
 bool make_wplan(const ConvArgs& a, WPlan& pl) {
-  if (a.Cin != CH || a.Cout != CH || a.cin_pad != CH || a.cout_pad != CH) return false;
+  if ((a.Cin != CH && a.Cin != 2 * CH) || a.Cout != a.Cin || a.cin_pad != a.Cin || a.cout_pad != a.Cin) return false;
+  pl.nh = a.Cin / CH;
   pl.SR = (TN + (a.k - 1) * a.dil) | 1;
-  pl.row_bytes = (uint32_t)CH * (a.x_f16 ? 2u : 4u);
+  pl.row_bytes = (uint32_t)CH * (a.x_f16 ? 2u : 4u);      // a unit's share of one row
   uint32_t off = 16;
   pl.off_bar = off; off += 8u * (2 * MAXSTAGE + 8 + 2 * MAXRAW);
   off = (off + 15u) & ~15u;
-  pl.off_par = off; off += 5u * CH * 4u;
+  pl.off_par = off; off += 5u * (uint32_t)a.Cin * 4u;
   off = (off + 127u) & ~127u;
   pl.off_slab = off;
   pl.slab_bytes = ((uint32_t)PLANES * pl.SR * 16u + 127u) & ~127u;
@@ -503,9 +532,31 @@ bool g_attr_set_wa[64] = {false};
 
 }  // namespace
 
+// The weights of a Cin = Cout = 128 NH layer in the order the MMA warp consumes them: [h][mt][tap][64-channel chunk], each stage
+// [8-channel plane][128 Cout rows][8 channels] (no-swizzle K-major, the A operand).  w: [k][C][ldw] fp32.  fmt: 0 = bf16, 1 = fp16.
+void pack_umma_wa_weights(const float* w, int k, int C, int ldw, int fmt, std::vector<uint16_t>& out) {
+  const int nh = C / CH;
+  out.assign((size_t)nh * nh * k * (CH / KCH) * CH * KCH, (uint16_t)0);
+  size_t base = 0;
+  for (int h = 0; h < nh; ++h)
+    for (int mt = 0; mt < nh; ++mt)
+      for (int j = 0; j < k; ++j)
+        for (int kc = 0; kc < CH / KCH; ++kc, base += (size_t)CH * KCH)
+          for (int pln = 0; pln < 8; ++pln)
+            for (int n = 0; n < CH; ++n)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = h * CH + kc * KCH + pln * 8 + e, co = mt * CH + n;
+                const float v = w[((size_t)j * C + ci) * ldw + co];
+                uint16_t bits;
+                if (fmt == 1) { const __half hv = __float2half(v); bits = *reinterpret_cast<const uint16_t*>(&hv); }
+                else { const __nv_bfloat16 bv = __float2bfloat16(v); bits = *reinterpret_cast<const uint16_t*>(&bv); }
+                out[base + ((size_t)pln * CH + n) * 8 + e] = bits;
+              }
+}
+
 bool conv_umma_wa_supported(const ConvArgs& a) {
   if (!a.wb || a.wfmt < 0 || a.wfmt > 1 || a.pro != PRO_ADAIN_SNAKE || a.stride != 1 || a.in_shr != 0 || a.act != ACT_NONE) return false;
-  if (a.tile_rows != TN || a.ldx != CH || a.ldy != CH || (a.res && a.ldr != CH)) return false;
+  if (a.tile_rows != TN || a.ldx != a.Cin || a.ldy != a.Cin || (a.res && a.ldr != a.Cin)) return false;
   if (a.acc_scale != 0.f && a.acc_scale != 1.0f) return false;
   if (reinterpret_cast<uintptr_t>(a.x) & 15) return false;
   if (a.y_f16 && (a.accumulate || a.out_scale != 1.0f)) return false;
@@ -524,12 +575,14 @@ cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
   u.a = a;
   if (!make_wplan(a, u.p)) return cudaErrorInvalidValue;
   using KernelFn = void (*)(const WArgs);
-  // [wfmt][x_f16][y_f16]: fp32 in / fp16 out = c1 of a block's first iteration; fp16 / fp16 = the other c1s and the c2s that write the
-  // block's running value; fp16 in / fp32 out = the last c2; fp32 / fp32 does not occur
-  static const KernelFn table[2][2][2] = {
-      {{nullptr, conv_umma_wa_kernel<0, false, true>}, {conv_umma_wa_kernel<0, true, false>, conv_umma_wa_kernel<0, true, true>}},
-      {{nullptr, conv_umma_wa_kernel<1, false, true>}, {conv_umma_wa_kernel<1, true, false>, conv_umma_wa_kernel<1, true, true>}}};
-  const KernelFn kernel = table[a.wfmt][a.x_f16 ? 1 : 0][a.y_f16 ? 1 : 0];
+  // [channels / 128 - 1][wfmt][x_f16][y_f16]: fp32 in / fp16 out = c1 of a block's first iteration; fp16 / fp16 = the other c1s and
+  // the c2s that write the block's running value; fp16 in / fp32 out = the last c2; fp32 / fp32 does not occur
+  static const KernelFn table[2][2][2][2] = {
+      {{{nullptr, conv_umma_wa_kernel<0, false, true, 1>}, {conv_umma_wa_kernel<0, true, false, 1>, conv_umma_wa_kernel<0, true, true, 1>}},
+       {{nullptr, conv_umma_wa_kernel<1, false, true, 1>}, {conv_umma_wa_kernel<1, true, false, 1>, conv_umma_wa_kernel<1, true, true, 1>}}},
+      {{{nullptr, conv_umma_wa_kernel<0, false, true, 2>}, {conv_umma_wa_kernel<0, true, false, 2>, conv_umma_wa_kernel<0, true, true, 2>}},
+       {{nullptr, conv_umma_wa_kernel<1, false, true, 2>}, {conv_umma_wa_kernel<1, true, false, 2>, conv_umma_wa_kernel<1, true, true, 2>}}}};
+  const KernelFn kernel = table[u.p.nh - 1][a.wfmt][a.x_f16 ? 1 : 0][a.y_f16 ? 1 : 0];
   if (!kernel) return cudaErrorInvalidValue;
   int dev = 0;
   {
@@ -538,13 +591,13 @@ cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
   }
   if (!g_attr_set_wa[dev]) {
-    for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 2; ++j)
-        for (int k = 0; k < 2; ++k)
-          if (table[i][j][k]) {
-            cudaError_t e = cudaFuncSetAttribute(table[i][j][k], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (e != cudaSuccess) return e;
-          }
+    for (int i = 0; i < 16; ++i) {
+      const KernelFn f = (&table[0][0][0][0])[i];
+      if (f) {
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+      }
+    }
     cudaError_t e = cudaDeviceGetAttribute(&g_num_sms_wa[dev], cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
     g_attr_set_wa[dev] = true;
@@ -556,8 +609,6 @@ cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
     if (prof_on && cudaMalloc(&prof_buf, sizeof(long long) * 16 * 256) != cudaSuccess) prof_on = 0;
   }
   u.prof = prof_on ? prof_buf : nullptr;
-  static const int l2pf = getenv("TTSB_L2PF") ? atoi(getenv("TTSB_L2PF")) : 0;
-  u.l2pf = (l2pf >> 1) & 1;
   const int ncta = u.p.items < g_num_sms_wa[dev] ? u.p.items : g_num_sms_wa[dev];      // persistent: one CTA per SM
   u.p.per_cta = (u.p.items + ncta - 1) / ncta;
   const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
@@ -579,8 +630,8 @@ cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
         for (int i = 0; i < 9; ++i) m[i] += (double)host[cta * 16 + i] / grid;
       float ms = 0.f;
       cudaEventElapsedTime(&ms, pe0, pe1);
-      fprintf(stderr, "umma_wa fmt=%d xh=%d yh=%d k=%d dil=%d grid=%d items/cta=%.1f SR=%d ring=%dx%uB wstages=%d | producer %.0f (wait %.0f) | mma %.0f (wait slab %.0f acc %.0f w %.0f) | epilogue %.0f (wait %.0f) cycles | %.1f us\n",
-              a.wfmt, a.x_f16, a.y_f16, a.k, a.dil, grid, m[8], u.p.SR, u.p.nraw, u.p.raw_bytes, u.p.nstage, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], ms * 1000.f);
+      fprintf(stderr, "umma_wa C=%d fmt=%d xh=%d yh=%d k=%d dil=%d grid=%d items/cta=%.1f SR=%d ring=%dx%uB wstages=%d | producer %.0f (wait %.0f) | mma %.0f (wait slab %.0f acc %.0f w %.0f) | epilogue %.0f (wait %.0f) cycles | %.1f us\n",
+              a.Cin, a.wfmt, a.x_f16, a.y_f16, a.k, a.dil, grid, m[8], u.p.SR, u.p.nraw, u.p.raw_bytes, u.p.nstage, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], ms * 1000.f);
     }
   }
   return launched();

@@ -158,7 +158,7 @@ struct Loader {
     return true;
   }
   // torch Conv1d weight [Cout, Cin, k] (or Linear [Cout, Cin]) -> ConvW
-  // want: bit 0 = 16-bit tensor-core packs (bf16 + fp16), bit 1 = split-fp16 pack (fp32-equivalent)
+  // want: bit 0 = 16-bit tensor-core packs (bf16 + fp16), bit 1 = split-fp16 pack (fp32-equivalent), bit 2 = weights-as-A packs (256 channels)
   void pack_conv(const HostTensor& w, const std::vector<float>* bias, ConvW& c, int want);
   bool conv(const std::string& prefix, ConvW& c, bool has_bias = true, int want = 0) {
     HostTensor w;
@@ -230,6 +230,12 @@ void Loader::pack_conv(const HostTensor& w, const std::vector<float>* bias, Conv
     pack_umma_weights(p.data(), k, Cin, Cout, c.ldw, 2, pb, c.cin_pad_s, c.cout_pad_s, &c.ws_scale);
     c.ws = upload(pb);
   }
+  if ((want & 4) && Cin == Cout && Cin == 256) {      // 256-channel resblock layers: the weights-as-A kernel's own stage order
+    pack_umma_wa_weights(p.data(), k, Cin, c.ldw, 0, pb);
+    c.wab = upload(pb);
+    pack_umma_wa_weights(p.data(), k, Cin, c.ldw, 1, pb);
+    c.wah = upload(pb);
+  }
 }
 
 bool Loader::lstm(const std::string& prefix, LstmW& l) {
@@ -278,7 +284,7 @@ bool Loader::resblock1(const std::string& prefix, ResBlock1W& r, int C, int k, s
   bool ok = true;
   for (int m = 0; m < 3 && ok; ++m) {
     const std::string i = std::to_string(m);
-    ok = ok && conv(prefix + ".convs1." + i, r.c1[m], true, 3) && conv(prefix + ".convs2." + i, r.c2[m], true, 3);
+    ok = ok && conv(prefix + ".convs1." + i, r.c1[m], true, 7) && conv(prefix + ".convs2." + i, r.c2[m], true, 7);
     ok = ok && style_fc(prefix + ".adain1." + i + ".fc", 2 * C, sw, sb, r.a1[m], C) && style_fc(prefix + ".adain2." + i + ".fc", 2 * C, sw, sb, r.a2[m], C);
     r.alpha1[m] = upload_named(prefix + ".alpha1." + i);
     r.alpha2[m] = upload_named(prefix + ".alpha2." + i);
@@ -595,6 +601,7 @@ int run_conv(Run& r, const ConvCall& c, const SegTab& t) {
   if (c.wa) {
     // the caller sized its buffers for this kernel (fp16 intermediate, 256-row tiles): no other kernel can take the call
     a.tile_rows = CONV_WA_TILE_ROWS; a.x_f16 = c.x_f16; a.y_f16 = c.y_f16; a.r_f16 = c.r_f16;
+    if (half16 && a.Cin == 256) a.wb = f16 ? c.w->wah : c.w->wab;        // that kernel's own stage order for two channel halves
     if (!half16 || !conv_umma_wa_supported(a)) { set_error("internal: weights-as-A conv kernel refused Cin=%d Cout=%d k=%d dil=%d", a.Cin, a.Cout, a.k, a.dil); return TTSB_E_INVALID; }
     const double rows_wa = (double)t.out_rows;
     r.e.prof.begin(r.s, PROF_CONV_TENSOR, 2.0 * rows_wa * a.Cin * a.Cout * a.k,
@@ -785,6 +792,9 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   static const bool no_wa = getenv("TTSB_NO_WA") != nullptr;
   const bool wa1 = !no_wa && (e.precision == TTSB_PRECISION_FP16 || e.precision == TTSB_PRECISION_BF16);
   const SegTab tS1w = wa1 ? r.make_tab(spS1, spS1, 1, 1, true, CONV_WA_TILE_ROWS) : SegTab();
+  static const bool no_wa0 = getenv("TTSB_NO_WA0") != nullptr;          // A/B: stage 0 on conv_umma_kernel
+  const bool wa0 = wa1 && !no_wa0;
+  const SegTab tS0w = wa0 ? r.make_tab(spS0, spS0, 1, 1, true, CONV_WA_TILE_ROWS) : SegTab();
   const SegTab tS1_A = r.make_tab(spS1, spA, 1, 1, false);
   // per-utterance seeds of the in-kernel SineGen noise (null: vocoder-only entry, noise keyed by position in the buffer)
   const unsigned long long* seg_seeds = (utt_seeds && (int)utt_seeds->size() == nseg) ? r.push(*utt_seeds) : nullptr;
@@ -816,7 +826,7 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
     //   b0: xs -> up -> acc (the stage's output, kept)    b1: xt (fp16 rows on the weights-as-A path)    b2: xs2 -> cur    b3: x0
     float* b0 = r.alloc<float>(std::max(n, nup));
     const Arena::Mark stage_scope = r.mark();                   // b1..b3 (and any operand-image scratch) go back at the end of the stage
-    const SegTab* twa = (i == 1 && wa1) ? &tS1w : nullptr;
+    const SegTab* twa = (i == 1 && wa1) ? &tS1w : (i == 0 && wa0) ? &tS0w : nullptr;
     float* b1 = twa ? reinterpret_cast<float*>(r.alloc<__half>(n)) : r.alloc<float>(n);
     float* b2 = r.alloc<float>(n);
     float* b3 = r.alloc<float>(n);

@@ -22,6 +22,7 @@ struct ConvW {
   uint16_t* wb = nullptr;                 // bf16 UMMA pack (see conv_umma.cu), or null
   uint16_t* wh = nullptr;                 // fp16 UMMA pack, or null
   uint16_t* ws = nullptr;                 // split-fp16 UMMA pack (hi | lo), or null: fp32-equivalent tensor-core path
+  uint16_t* wab = nullptr, *wah = nullptr; // bf16 / fp16 packs in conv_umma_wa.cu's stage order (256-channel resblock layers), or null
   int cin_pad = 0, cout_pad = 0;
   int cin_pad_s = 0, cout_pad_s = 0;
   float ws_scale = 0.f;                   // power of two the split pack's weights were scaled by (chosen from max|w| of the layer)
