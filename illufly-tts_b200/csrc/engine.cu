@@ -793,6 +793,11 @@ int run_generator(Run& r, const Space& spL, const float* gen_in, const float* f0
   const bool wa1 = !no_wa && (e.precision == TTSB_PRECISION_FP16 || e.precision == TTSB_PRECISION_BF16);
   const SegTab tS1w = wa1 ? r.make_tab(spS1, spS1, 1, 1, true, CONV_WA_TILE_ROWS) : SegTab();
   static const bool no_wa0 = getenv("TTSB_NO_WA0") != nullptr;          // A/B: stage 0 on conv_umma_kernel
+  // Stage 0 is on that kernel whatever the batch: choosing by size would be faster for short inputs (one 256-row tile of 256 channels
+  // is ~50 k cycles of MMAs (k11) against ~30 k for a 128-row tile of conv_umma_kernel, so with at most one tile per SM either way the
+  // smaller tile finishes first: configs[0] 4.09 ms against 4.38 ms) but the two kernels keep different intermediates (fp16 against
+  // fp32), and a request must give the same waveform alone and inside a batch (test_service_is_a_pure_scheduler_and_batch_invariant).
+  // TTSB_NO_WA0=1 selects the 128-row kernel for a whole process (a latency-first deployment).
   const bool wa0 = wa1 && !no_wa0;
   const SegTab tS0w = wa0 ? r.make_tab(spS0, spS0, 1, 1, true, CONV_WA_TILE_ROWS) : SegTab();
   const SegTab tS1_A = r.make_tab(spS1, spA, 1, 1, false);
