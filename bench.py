@@ -357,8 +357,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3) if args.workload == "batch32" else max(args.warmup, 1)
     prec = {"f16": pkg.PRECISION_FP16, "bf16": pkg.PRECISION_BF16, "fp32": pkg.PRECISION_FP32}[args.precision]
-    tier = {"f16": "tcgen05, fp16 operands, fp32 accumulate (the north star's >= 40 dB tier: 60.8 dB measured)",
-            "bf16": "tcgen05, bf16 operands, fp32 accumulate (>= 40 dB tier: 42.9 dB measured)",
+    tier = {"f16": "tcgen05, fp16 operands, fp32 accumulate (the north star's >= 40 dB tier: 59.1 dB measured on bit-identical generator inputs)",
+            "bf16": "tcgen05, bf16 operands, fp32 accumulate (>= 40 dB tier: 42.8 dB measured)",
             "fp32": "the strict tier (max-abs 1e-3): tcgen05, split-fp16 operands (x = hi + lo, 3 MMAs per K step), fp32 accumulate"}[args.precision]
 
     ckpt = synthetic_checkpoint(1234)                                   # random-init weights of the Kokoro-82M architecture
