@@ -1,9 +1,10 @@
-// tcgen05 implicit-GEMM Conv1d for the 128-channel layers (stage 1 of the generator: 24 of the 48 resblock convs, 46 % of the
-// conv time of a step), with the WEIGHTS as the A operand:
+// tcgen05 implicit-GEMM Conv1d for the AdaINResBlock1 layers of the generator (48 of a step's 144 conv launches, 53 % of the step's
+// kernel time: stage 1 with 128 channels, stage 0 with 256), with the WEIGHTS as the A operand:
 //
 //   D[Cout (M = 128 TMEM lanes), time (N = 256 TMEM columns)] += W[tap][Cout, Cin chunk] * X[time + tap*dil - pad, Cin chunk]^T
 //
-// Why the roles are swapped relative to conv_umma.cu.  There the time axis is M (128 rows) and Cout is N; for Cout = 128 an
+// Why the roles are swapped relative to conv_umma.cu (written for 128 channels; the 256-channel case is at the end of this comment).
+// There the time axis is M (128 rows) and Cout is N; for Cout = 128 an
 // M128 x N128 x K16 MMA lasts 64 tensor cycles and reads 4 KB of A and 4 KB of B from shared memory: 128 B/clk, the SM's whole
 // shared-memory bandwidth, before the producers, the weight stream and the epilogue staging get any (ncu, round 1:
 // sm__pipe_tensor_cycles_active 13-41 % on these layers).  With the weights as A and 256 time rows as N the MMA lasts 128
