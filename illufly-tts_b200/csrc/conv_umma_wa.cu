@@ -65,6 +65,7 @@ struct WPlan {
   int nstage, nraw, rps, rch, nch;      // weight stages; ring slots, rows per producer thread per slot, rows per slot, slots per slab
   int items, per_cta;
   int nh;                               // 128-channel halves: 1 (128-channel layers) or 2 (256)
+  int split;                            // nh = 2, few tiles: a work item is (tile, output half) - twice the CTAs, half the MMAs each
   uint32_t off_bar, off_par, off_slab, slab_bytes, off_raw, raw_bytes, off_w, smem_bytes, row_bytes;
 };
 
@@ -164,6 +165,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
 
   const int item0 = blockIdx.x * pl.per_cta;
   const int item1 = min(item0 + pl.per_cta, pl.items);
+  // split mode (256 channels, fewer tiles than half the SMs): item = 2 tile + output half.  The accumulation of an output half is the
+  // same sequence of MMAs either way (for h: for tap), so the results do not depend on the mode - a request gives the same samples
+  // alone (split) and inside a large batch (not split).
+  const bool split = NH > 1 && pl.split != 0;
+  const int nmt = split ? 1 : NH;                    // output halves per work item
+  auto tile_of = [&](int item) { return split ? (item >> 1) : item; };
+  auto mt_of = [&](int item) { return split ? (item & 1) : 0; };
 
   // ---- one-time setup ----
   if (warp == 9) tmem_alloc(smem_u32(s_tmem), 512u);
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
       for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
     };
     for (int item = item0; item < item1; ++item, ++n) {
-      const Tile tile = p.tiles[item];
+      const Tile tile = p.tiles[tile_of(item)];
       const Seg seg = p.segs[tile.seg];
       const bool new_seg = tile.seg != cur_seg;
       if (new_seg) {
@@ -308,14 +316,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     // =================== weight loader (bulk-copy engine) ===================
     if (lane == 0) {
       uint32_t it = 0;
-      const int nblk = NH * NH * p.k * (CH / KCH);       // stages per tile, in pack order [h][mt][tap][64-channel chunk]
-      for (int item = item0; item < item1; ++item)
-        for (int blk = 0; blk < nblk; ++blk, ++it) {
-          const uint32_t s = it % NS;
-          mbar_wait(bar_empty(s), ((it / NS) & 1u) ^ 1u);
-          mbar_expect_tx(bar_full(s), WSTAGE_BYTES);
-          bulk_g2s(w0 + s * WSTAGE_BYTES, p.wb + (size_t)blk * (WSTAGE_BYTES / 2), WSTAGE_BYTES, bar_full(s));
-        }
+      // stages in pack order [h][mt][tap][64-channel chunk]; an item takes the output halves [mt0, mt0 + nmt) of both input halves
+      for (int item = item0; item < item1; ++item) {
+        const int mt0 = mt_of(item);
+        for (int h = 0; h < NH; ++h)
+          for (int mt = mt0; mt < mt0 + nmt; ++mt)
+            for (int jk = 0; jk < p.k * (CH / KCH); ++jk, ++it) {
+              const uint32_t s = it % NS;
+              const size_t blk = (size_t)((h * NH + mt) * p.k * (CH / KCH) + jk);
+              mbar_wait(bar_empty(s), ((it / NS) & 1u) ^ 1u);
+              mbar_expect_tx(bar_full(s), WSTAGE_BYTES);
+              bulk_g2s(w0 + s * WSTAGE_BYTES, p.wb + blk * (WSTAGE_BYTES / 2), WSTAGE_BYTES, bar_full(s));
+            }
+      }
     }
   } else if (warp == 9) {
     // =================== MMA issuer ===================
@@ -334,6 +347,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     long long tw_slab = 0, tw_acc = 0, tw_w = 0;
     const long long t_start = clock64();
     for (int item = item0; item < item1; ++item, ++n) {
+      const int mt0 = mt_of(item);
 #pragma unroll 1
       for (int h = 0; h < NH; ++h) {
         const uint32_t uc = n * NH + h;                  // unit: one 128-channel half of the tile's input rows
@@ -342,8 +356,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
         tc_fence_after();
         const uint32_t sbase = slab0 + sl * pl.slab_bytes;
 #pragma unroll 1
-        for (int mt = 0; mt < NH; ++mt) {
-          const uint32_t g = n * NH + mt;                // accumulation: one 128-channel half of the tile's outputs
+        for (int mt = mt0; mt < mt0 + nmt; ++mt) {
+          const uint32_t g = n * (uint32_t)nmt + (uint32_t)(mt - mt0);      // accumulation: one 128-channel half of the tile's outputs
           const uint32_t slot = g & 1u;
           if (h == 0) {
             mbar_wait_t(bar_acc_empty(slot), ((g >> 1) & 1u) ^ 1u, tw_acc);       // epilogue has drained this accumulator
@@ -387,7 +401,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     const uint32_t ubytes = (uint32_t)CH * ESZ;              // a unit's share of one row
     for (int item = item0; item < item1; ++item) {
       if (pl.nraw == 0) continue;
-      const Tile tile = p.tiles[item];
+      const Tile tile = p.tiles[tile_of(item)];
       const Seg seg = p.segs[tile.seg];
       const int row_lo = tile.t0 - p.pad;
       if (!(row_lo >= 0 && row_lo + SR <= seg.in_len)) continue;      // edge tile: the producers load it themselves
@@ -424,14 +438,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
     long long tw_full = 0;
     const long long t_start = clock64();
     for (int item = item0; item < item1; ++item, ++n) {
-      const Tile tile = p.tiles[item];
+      const Tile tile = p.tiles[tile_of(item)];
       const Seg seg = p.segs[tile.seg];
+      const int mt0 = mt_of(item);
       const int tbase = tile.t0 + half * 128;
       const int nv = seg.out_len - tbase;              // rows of this half tile inside the utterance (<= 0: nothing to store)
       const size_t row0 = (size_t)(seg.out_off + tbase);
 #pragma unroll 1
-      for (int mt = 0; mt < NH; ++mt) {
-        const uint32_t g = n * NH + mt;                // accumulation number: slot = low bit, phase = next bit
+      for (int mt = mt0; mt < mt0 + nmt; ++mt) {
+        const uint32_t g = n * (uint32_t)nmt + (uint32_t)(mt - mt0);        // accumulation number: slot = low bit, phase = next bit
         const uint32_t slot = g & 1u;
         const int c = mt * CH + cl;
         const float bs = mt ? bias1 : bias0;
@@ -463,7 +478,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_umma_wa_kernel(const WArgs u
       }
       if (p.ostats) {
         // flush this thread's running sums when the utterance changes or the CTA is done
-        const bool flush = item + 1 >= item1 || p.tiles[item + 1].seg != tile.seg;
+        const bool flush = item + 1 >= item1 || p.tiles[tile_of(item + 1)].seg != tile.seg;
         if (flush) {
           double* st = p.ostats + ((size_t)tile.seg * p.ld_ostats + cl) * 2;
           atomicAdd(st, dsum0);
@@ -525,6 +540,7 @@ bool make_wplan(const ConvArgs& a, WPlan& pl) {
   (void)nstage_min;
   pl.smem_bytes = pl.off_w + pl.nstage * WSTAGE_BYTES;
   pl.items = a.ntiles;
+  pl.split = 0;
   return pl.smem_bytes <= limit;
 }
 
@@ -610,6 +626,10 @@ cudaError_t launch_conv_umma_wa(const ConvArgs& a, cudaStream_t s) {
     if (prof_on && cudaMalloc(&prof_buf, sizeof(long long) * 16 * 256) != cudaSuccess) prof_on = 0;
   }
   u.prof = prof_on ? prof_buf : nullptr;
+  // few 256-channel tiles (single requests, short batches): one work item per (tile, output half), so that twice as many SMs share
+  // the MMAs (a k11 tile is 45 k cycles of them); bit-identical results (see the kernel)
+  static const bool no_split = getenv("TTSB_WA_NOSPLIT") != nullptr;
+  if (u.p.nh == 2 && !no_split && 2 * u.p.items <= g_num_sms_wa[dev]) { u.p.split = 1; u.p.items *= 2; }
   const int ncta = u.p.items < g_num_sms_wa[dev] ? u.p.items : g_num_sms_wa[dev];      // persistent: one CTA per SM
   u.p.per_cta = (u.p.items + ncta - 1) / ncta;
   const int grid = (u.p.items + u.p.per_cta - 1) / u.p.per_cta;
