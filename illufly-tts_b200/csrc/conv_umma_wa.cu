@@ -33,6 +33,8 @@
 // g = n NH + mt; their barrier slot is the number's low bit and the phase the next bit - for NH = 1 exactly the two-slot scheme above.
 // The weights come in pack order [h][mt][tap][64-channel chunk] (pack_umma_wa_weights), 16 KB per stage as before; the raw-row ring
 // takes the unit's 128 channels of each row (one bulk copy per row, the lanes of the row loader side by side).
+// When the tiles are fewer than half the SMs (single requests) a work item is (tile, output half mt): two CTAs build the same slabs and
+// each runs its half's MMAs - the same sequence per accumulator, so the results are the same bits as in the one-CTA-per-tile mode.
 #include "common.cuh"
 #include "umma_ptx.cuh"
 
