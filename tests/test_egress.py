@@ -1,6 +1,8 @@
 """Audio egress: the in-memory float32 RIFF/WAVE image against the one byte-level fact the reference tree
 holds - the response logged at /root/reference/service.log:33 (650,480 bytes, base64 prefix ``UklGRujsCQ``) - and round trips."""
 import base64
+import json
+import os
 import struct
 
 import torch
@@ -8,15 +10,23 @@ import torch
 from illufly_tts_b200.egress import HEADER_BYTES, read_wav_float32, wav_base64, wav_float32_bytes
 
 
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_service_log.json")))
+
+
 def test_size_and_prefix_of_the_logged_reference_response():
-    """service.log:33 shows a RIFF of 650,480 bytes whose base64 starts with UklGRujsCQ.  162,600 samples (= 600 x 271 frames, the
-    only float-WAV header size that leaves a whole number of 600-sample frames) written here give exactly that size and prefix."""
-    audio = torch.zeros(600 * 271)
+    """service.log:33 shows a RIFF of 650,480 bytes whose base64 starts with UklGRujsCQ (tests/golden/reference_service_log.json,
+    extracted from the reference tree by tests/golden/make_reference_log_fixture.py).  162,600 samples (= 600 x 271 frames, the only
+    float-WAV header size that leaves a whole number of 600-sample frames) written here give exactly that size and prefix."""
+    assert GOLDEN["audio_base64_prefix"] == "UklGRujsCQ" and GOLDEN["file_bytes"] == 650_480        # the fixture is what the survey read
+    n = (GOLDEN["file_bytes"] - HEADER_BYTES) // 4
+    assert n == 600 * 271 and HEADER_BYTES == 80
+    audio = torch.zeros(n)
     blob = wav_float32_bytes(audio, 24000, timestamp=0)
-    assert len(blob) == 650_480 and HEADER_BYTES == 80
-    assert struct.unpack_from("<I", blob, 4)[0] == 0x0009ECE8
-    assert base64.b64encode(blob).decode()[:10] == "UklGRujsCQ"
-    assert wav_base64(audio, 24000, timestamp=0)[:10] == "UklGRujsCQ"
+    assert len(blob) == GOLDEN["file_bytes"]
+    assert struct.unpack_from("<I", blob, 4)[0] == GOLDEN["riff_size_field"] == 0x0009ECE8
+    assert blob[:7].hex() == GOLDEN["decoded_hex"]
+    assert base64.b64encode(blob).decode()[:10] == GOLDEN["audio_base64_prefix"]
+    assert wav_base64(audio, 24000, timestamp=0)[:10] == GOLDEN["audio_base64_prefix"]
 
 
 def test_header_fields_and_round_trip():

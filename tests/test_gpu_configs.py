@@ -5,6 +5,8 @@ on the engine's own generator inputs) AND records the plain end-to-end compariso
 nothing substituted).  Measured numbers go to the parity report (tests/parity.py::record -> profiles/r02_parity.md).
 
 The frame-side tap bars below are the values MEASURED on B200 (profiles/r02_parity.md) times two."""
+import os
+
 import pytest
 import torch
 
@@ -109,3 +111,25 @@ def test_config3_vocoder_cell_b16_l1000(engine, oracle, mode):
             a = audio[b].cpu()
             e2e.append(dict(max_abs=float((a - ref).abs().max()), snr=snr_db(ref, a), n=a.numel()))
     record("configs[3] vocoder B=16 L=1000", mode, utterances=B, frames=B * L, back=summarise(back), e2e=summarise(e2e))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "f16"])
+def test_engine_durations_equal_the_committed_vectors(engine, mode):
+    """tests/golden/oracle_outputs.json: integer durations (and so frame and sample counts) of configs[0] and of three utterances of
+    configs[1], committed - the engine must reproduce them with no oracle run in the loop, in the strict and in the 16-bit mode (the
+    text side is fp32-class in both)."""
+    import importlib.util
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = json.load(open(os.path.join(here, "oracle_outputs.json")))["cases"]
+    spec = importlib.util.spec_from_file_location("make_oracle_fixture", os.path.join(here, "make_oracle_fixture.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    engine.set_precision(MODES[mode])
+    try:
+        for name, w in mod.cases().items():
+            r = engine.synthesize(w["ids"], w["ref_s"], w["speeds"], seed=1)
+            assert [[int(v) for v in p.tolist()] for p in r.pred_dur] == gold[name]["pred_dur"], name
+            assert [int(a.numel()) for a in r.audio] == [600 * f for f in gold[name]["frames"]], name
+    finally:
+        engine.set_precision(pkg.PRECISION_FP32)

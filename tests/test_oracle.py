@@ -124,3 +124,26 @@ def test_noise_is_reproducible():
     assert torch.equal(make_noise(0, 3, 5), make_noise(0, 3, 5))
     assert make_noise(0, 3, 5).shape == (3000, 9)
     assert math.isclose(float(make_noise(1, 0, 50).std()), 1.0, rel_tol=0.02)
+
+
+def test_oracle_reproduces_the_committed_outputs(oracle):
+    """tests/golden/oracle_outputs.json (tests/golden/make_oracle_fixture.py): the oracle on configs[0] and on three utterances of
+    configs[1].  Integer durations must come out exactly; tap and waveform statistics within float noise of another machine's BLAS.
+    This pins the oracle against itself - not against the reference, which holds no vectors for this path."""
+    import importlib.util
+    import json
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = json.load(open(os.path.join(here, "oracle_outputs.json")))["cases"]
+    spec = importlib.util.spec_from_file_location("make_oracle_fixture", os.path.join(here, "make_oracle_fixture.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name, w in mod.cases().items():
+        o = oracle.forward_batch(w["ids"], w["ref_s"], w["speeds"], noise_seed=0, want_taps=True)
+        got, ref = mod.summarise(o), gold[name]
+        assert got["pred_dur"] == ref["pred_dur"], name
+        for k, s in ref["taps"].items():
+            assert got["taps"][k]["shape"] == s["shape"]
+            assert abs(got["taps"][k]["mean_abs"] - s["mean_abs"]) <= 1e-4 * s["mean_abs"], (name, k)
+        for a, b in zip(got["audio"], ref["audio"]):
+            assert a["samples"] == b["samples"] and abs(a["mean_abs"] - b["mean_abs"]) <= 2e-2 * b["mean_abs"], name
