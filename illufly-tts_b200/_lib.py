@@ -33,6 +33,8 @@ SIGNATURES = {
     "ttsb_engine_profile": (C.c_int, [_p, C.c_int]),
     "ttsb_engine_profile_read": (C.c_int, [_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _i64p]),
     "ttsb_synthesize_begin": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p]),
+    "ttsb_engine_voice_pack_set": (C.c_int, [_p, C.c_int, _p, C.c_int]),
+    "ttsb_synthesize_begin_voices": (C.c_int, [_p, _p, _p, C.c_int, _p, _p, _p, C.c_int, _p, _p, _p, _p]),
     "ttsb_synthesize_finish": (C.c_int, [_p, _p, C.c_int, C.c_uint64, _p, _p, C.c_int]),
     "ttsb_vocoder": (C.c_int, [_p, _p, _p, _p, _p, C.c_int, C.c_int, _p, C.c_uint64, _p, C.c_int]),
     "ttsb_engine_read_tap": (C.c_int, [_p, C.c_char_p, _p, _i64p, _i64p]),

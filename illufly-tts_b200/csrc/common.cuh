@@ -125,6 +125,7 @@ cudaError_t launch_duration(const float* logits, int ld, int nbins, const int* r
                             int rows, cudaStream_t s);
 cudaError_t launch_dur_scan(const int* pred_dur, const Seg* segs, int nseg, int* cum, int* totals, cudaStream_t s);
 cudaError_t launch_indices(const int* cum, const Seg* segs, int nseg, int* indices, int total_frames, const int* frame2seg, cudaStream_t s);
+cudaError_t launch_gather_ptr_rows(const float* const* src, float* dst, int C, int rows, cudaStream_t s);
 cudaError_t launch_gather_rows(const float* src, int lds, const int* indices, const int* frame2seg, const Seg* segs, float* dst, int ldd,
                                int C, int rows, cudaStream_t s);
 cudaError_t launch_colstats(const float* x, int ldx, int C, const Seg* segs, int nseg, int max_len, double* stats, int ld_stats, cudaStream_t s);

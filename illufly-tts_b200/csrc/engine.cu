@@ -908,9 +908,20 @@ int run_style(Run& r, const ConvW& w, const float* style, int ld_style, int nseg
 // begin(): token side, kmodel.py:62-119
 // ======================================================================================================
 int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, int B, const float* ref_s, const float* speeds, int padded_lstm,
-                 const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets) {
+                 const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets, const int32_t* voice_slot,
+                 const int32_t* voice_row) {
   if (!e.finalized) { set_error("begin: engine not finalized"); return TTSB_E_STATE; }
-  if (B <= 0 || !ids || !token_offsets || !ref_s || !pred_dur || !frame_offsets) { set_error("begin: bad arguments"); return TTSB_E_INVALID; }
+  const bool by_voice = voice_slot != nullptr;       // style rows come from voice packs resident on the device (ttsb_engine_voice_pack_set)
+  if (B <= 0 || !ids || !token_offsets || (!ref_s && !by_voice) || (by_voice && !voice_row) || !pred_dur || !frame_offsets) {
+    set_error("begin: bad arguments");
+    return TTSB_E_INVALID;
+  }
+  if (by_voice)
+    for (int b = 0; b < B; ++b) {
+      const int sl = voice_slot[b];
+      if (sl < 0 || sl >= (int)e.voice_pack.size() || !e.voice_pack[sl]) { set_error("begin: utterance %d names voice slot %d, which holds no pack", b, sl); return TTSB_E_INVALID; }
+      if (voice_row[b] < 0 || voice_row[b] >= e.voice_pack_rows[sl]) { set_error("begin: utterance %d asks for row %d of a %d-row voice pack", b, voice_row[b], e.voice_pack_rows[sl]); return TTSB_E_INVALID; }
+    }
   CK(cudaSetDevice(e.device));
   e.begun = false;
   CK(cudaStreamSynchronize(e.stream2));      // idle unless the previous step failed between a fork and its join: the workspace is about to be reused
@@ -955,7 +966,14 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
     e.utt_key[b] = hsh;
   }
   std::vector<LstmSeg> ls(B), lsq(B);
-  std::vector<float> h_speed(B), h_ref(ref_s, ref_s + (size_t)B * 256);
+  std::vector<float> h_speed(B), h_ref;
+  std::vector<const float*> h_refsrc;                    // by_voice: device address of every utterance's style row
+  if (by_voice) {
+    h_refsrc.resize(B);
+    for (int b = 0; b < B; ++b) h_refsrc[b] = e.voice_pack[voice_slot[b]] + (size_t)voice_row[b] * 256;
+  } else {
+    h_ref.assign(ref_s, ref_s + (size_t)B * 256);
+  }
   for (int b = 0; b < B; ++b) {
     for (int t = 0; t < lens[b]; ++t) { h_pos[e.spT.off[b] + t] = t; h_r2s[e.spT.off[b] + t] = b; }
     ls[b] = {e.spT.off[b], lens[b], 0};
@@ -970,11 +988,18 @@ int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, in
   const LstmGroup* d_lsq = r.push(g_lsq);
   const int n_ls = (int)g_ls.size();
   const float* d_speed = r.push(h_speed);
-  const float* d_ref = r.push(h_ref);
+  const float* d_ref = by_voice ? nullptr : r.push(h_ref);
+  const float* const* d_refsrc = by_voice ? r.push(h_refsrc) : nullptr;
   std::vector<int> h_forced;
   const int* d_forced = nullptr;
   if (forced_dur) { h_forced.assign(forced_dur, forced_dur + R); d_forced = r.push(h_forced); }
   RC(r.tables_upload());
+  if (by_voice) {                                       // gather the rows on the device: no style bytes cross PCIe
+    float* g = r.alloc<float>((size_t)B * 256);
+    if (!g) return TTSB_E_NOMEM;
+    CK(launch_gather_ptr_rows(d_refsrc, g, 256, B, r.s));
+    d_ref = g;
+  }
   e.d_refs = const_cast<float*>(d_ref);
   e.d_row2segT = const_cast<int*>(d_r2s);
   const SegTab& tT = e.tabT;

@@ -130,6 +130,9 @@ struct Engine {
   bool taps_on = false;
   cudaEvent_t ev_gap0 = nullptr, ev_gap1 = nullptr;   // TTSB_GAP_PROF=1: GPU idle time between the two halves of a step
   std::vector<unsigned long long> utt_key;   // per utterance of the step in flight: hash of its token ids (begin -> finish)
+  // voice packs resident in device memory: slot -> [rows, 256] fp32; begin() can take (slot, row) per utterance
+  std::vector<float*> voice_pack;
+  std::vector<int> voice_pack_rows;
   bool finalized = false;
   std::map<std::string, HostTensor> host;       // raw checkpoint tensors until finalize()
   std::vector<void*> dev_allocs;                // weights
@@ -176,7 +179,8 @@ struct Engine {
 // implemented in engine.cu
 int engine_finalize(Engine& e);
 int engine_begin(Engine& e, const int32_t* ids, const int32_t* token_offsets, int B, const float* ref_s, const float* speeds,
-                 int padded_lstm, const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets);
+                 int padded_lstm, const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets,
+                 const int32_t* voice_slot = nullptr, const int32_t* voice_row = nullptr);   // (slot, row) of a resident voice pack instead of ref_s
 int engine_finish(Engine& e, const float* noise, int noise_mem, uint64_t seed, int32_t* indices, float* audio, int audio_mem);
 int engine_vocoder(Engine& e, const float* x, const float* f0, const float* style, const int32_t* l_offsets, int B, int in_mem,
                    const float* noise, uint64_t seed, float* audio, int audio_mem);

@@ -132,6 +132,7 @@ int ttsb_engine_destroy(ttsb_engine* h) {
   if (e.stream) cudaStreamSynchronize(e.stream);
   if (e.stream2) cudaStreamSynchronize(e.stream2);
   for (void* p : e.dev_allocs) cudaFree(p);
+  for (float* p : e.voice_pack) if (p) cudaFree(p);
   for (auto& kv : e.taps) if (kv.second.d) cudaFree(kv.second.d);
   e.arena.release();
   if (e.pinned) cudaFreeHost(e.pinned);
@@ -215,6 +216,33 @@ int ttsb_synthesize_begin(ttsb_engine* h, const int32_t* ids, const int32_t* tok
                           int padded_lstm, const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets) {
   if (!h) { set_error("begin: engine is NULL"); return TTSB_E_INVALID; }
   GUARD("begin", return engine_begin(h->e, ids, token_offsets, B, ref_s, speeds, padded_lstm, forced_dur, pred_dur, duration, frame_offsets);)
+}
+
+// ---- voice packs resident on the device ----
+constexpr int TTSB_MAX_VOICE_SLOTS = 4096;
+int ttsb_engine_voice_pack_set(ttsb_engine* h, int slot, const float* pack, int rows) {
+  if (!h) { set_error("voice_pack_set: engine is NULL"); return TTSB_E_INVALID; }
+  GUARD("voice_pack_set",
+    Engine& e = h->e;
+    if (slot < 0 || slot >= TTSB_MAX_VOICE_SLOTS || (pack && (rows < 1 || rows > 65536))) { set_error("voice_pack_set: slot %d / rows %d out of range", slot, rows); return TTSB_E_INVALID; }
+    CKA(cudaSetDevice(e.device));
+    // a step in flight has gathered its rows before begin() returned (begin ends with a host synchronisation), so a pack can be replaced
+    // between calls; callers of one engine are serialised by the host side
+    if ((int)e.voice_pack.size() <= slot) { e.voice_pack.resize(slot + 1, nullptr); e.voice_pack_rows.resize(slot + 1, 0); }
+    if (e.voice_pack[slot]) { CKA(cudaStreamSynchronize(e.stream)); cudaFree(e.voice_pack[slot]); e.voice_pack[slot] = nullptr; e.voice_pack_rows[slot] = 0; }
+    if (!pack) return TTSB_OK;                           // NULL pack: the slot is emptied
+    float* d = nullptr;
+    if (cudaMalloc(&d, sizeof(float) * (size_t)rows * 256) != cudaSuccess) { cudaGetLastError(); set_error("voice_pack_set: out of device memory"); return TTSB_E_NOMEM; }
+    if (cudaMemcpy(d, pack, sizeof(float) * (size_t)rows * 256, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); cudaGetLastError(); set_error("voice_pack_set: copy failed"); return TTSB_E_CUDA; }
+    e.voice_pack[slot] = d; e.voice_pack_rows[slot] = rows;
+    return TTSB_OK;)
+}
+
+int ttsb_synthesize_begin_voices(ttsb_engine* h, const int32_t* ids, const int32_t* token_offsets, int B, const int32_t* voice_slot, const int32_t* voice_row,
+                                 const float* speeds, int padded_lstm, const int32_t* forced_dur, int32_t* pred_dur, float* duration, int32_t* frame_offsets) {
+  if (!h) { set_error("begin_voices: engine is NULL"); return TTSB_E_INVALID; }
+  if (!voice_slot || !voice_row) { set_error("begin_voices: voice_slot / voice_row is NULL"); return TTSB_E_INVALID; }
+  GUARD("begin_voices", return engine_begin(h->e, ids, token_offsets, B, nullptr, speeds, padded_lstm, forced_dur, pred_dur, duration, frame_offsets, voice_slot, voice_row);)
 }
 
 int ttsb_synthesize_finish(ttsb_engine* h, const float* noise, int noise_mem, uint64_t seed, int32_t* indices, float* audio, int audio_mem) {

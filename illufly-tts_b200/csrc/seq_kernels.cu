@@ -434,4 +434,15 @@ cudaError_t launch_gather_rows(const float* src, int lds, const int* indices, co
   return launched();
 }
 
+// style rows of resident voice packs: dst[b, :] = *src[b]  (src[b] = device address of pack[slot_b][row_b])
+__global__ void gather_ptr_rows_kernel(const float* const* __restrict__ src, float* __restrict__ dst, int C) {
+  const float* row = src[blockIdx.x];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dst[(size_t)blockIdx.x * C + c] = row[c];
+}
+cudaError_t launch_gather_ptr_rows(const float* const* src, float* dst, int C, int rows, cudaStream_t s) {
+  if (rows <= 0) return cudaSuccess;
+  gather_ptr_rows_kernel<<<rows, 256, 0, s>>>(src, dst, C);
+  return launched();
+}
+
 }  // namespace ttsb

@@ -149,11 +149,28 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------
     @_serialised
-    def synthesize(self, ids_list: Sequence[Sequence[int]], ref_s: torch.Tensor, speeds: Optional[Sequence[float]] = None,
+    def set_voice_pack(self, slot: int, pack: Optional[torch.Tensor]) -> int:
+        """Upload a voice pack ([rows,1,256] or [rows,256], the reference's ``voices[voice_id]``, pipeline.py:78-109) into device slot
+        ``slot`` - once; ``synthesize(voice_slots=..., voice_rows=...)`` then picks style rows on the device.
+        ``pack=None`` empties the slot.  Returns the number of rows."""
+        if pack is None:
+            _lib.check(self._lib.ttsb_engine_voice_pack_set(self._h, int(slot), None, 0))
+            return 0
+        p = pack.detach().to(torch.float32).reshape(pack.shape[0], -1).cpu()
+        if p.shape[1] != 256:
+            raise ValueError(f"a voice pack is [rows,1,256] or [rows,256]; got {tuple(pack.shape)}")
+        arr = np.ascontiguousarray(p.numpy())
+        _lib.check(self._lib.ttsb_engine_voice_pack_set(self._h, int(slot), _ptr(arr), int(arr.shape[0])))
+        return int(arr.shape[0])
+
+    @_serialised
+    def synthesize(self, ids_list: Sequence[Sequence[int]], ref_s: Optional[torch.Tensor], speeds: Optional[Sequence[float]] = None,
                    noise: Optional[Sequence[torch.Tensor]] = None, seed: int = 0, padded_lstm: bool = True,
                    want_indices: bool = False, forced_dur: Optional[Sequence[Sequence[int]]] = None,
-                   audio_to_host: bool = False) -> SynthesisResult:
-        """ids_list[b] already carries BOS/EOS (kmodel.py:36-42).  ref_s [B,256] or [B,1,256] (any device)."""
+                   audio_to_host: bool = False, voice_slots: Optional[Sequence[int]] = None,
+                   voice_rows: Optional[Sequence[int]] = None) -> SynthesisResult:
+        """ids_list[b] already carries BOS/EOS (kmodel.py:36-42).  ref_s [B,256] or [B,1,256] (any device) - or, with resident voice
+        packs (``set_voice_pack``), ``voice_slots`` / ``voice_rows`` per utterance and ``ref_s=None``."""
         B = len(ids_list)
         if B == 0:
             return SynthesisResult([], [], [], [])
@@ -161,12 +178,21 @@ class Engine:
         tok_off = np.zeros(B + 1, np.int32)
         np.cumsum(lens, out=tok_off[1:])
         ids = np.concatenate([np.asarray(x, np.int32) for x in ids_list]).astype(np.int32, copy=False)
-        ref = ref_s.detach()
-        if ref.dim() == 3:
-            ref = ref.squeeze(1)
-        ref = np.ascontiguousarray(ref.to(torch.float32).cpu().numpy())
-        if ref.shape != (B, 256):
-            raise ValueError(f"ref_s must be [B,256] or [B,1,256]; got {tuple(ref_s.shape)} for B={B}")
+        by_voice = voice_slots is not None
+        if by_voice:
+            if voice_rows is None or len(voice_slots) != B or len(voice_rows) != B:
+                raise ValueError("voice_slots and voice_rows must both give one entry per utterance")
+            vs = np.asarray(list(voice_slots), np.int32)
+            vr = np.asarray(list(voice_rows), np.int32)
+        else:
+            if ref_s is None:
+                raise ValueError("ref_s is required unless voice_slots / voice_rows are given")
+            ref = ref_s.detach()
+            if ref.dim() == 3:
+                ref = ref.squeeze(1)
+            ref = np.ascontiguousarray(ref.to(torch.float32).cpu().numpy())
+            if ref.shape != (B, 256):
+                raise ValueError(f"ref_s must be [B,256] or [B,1,256]; got {tuple(ref_s.shape)} for B={B}")
         sp = np.asarray([1.0] * B if speeds is None else list(speeds), np.float32)
         R = int(tok_off[-1])
         pred = np.empty(R, np.int32)
@@ -177,8 +203,12 @@ class Engine:
             forced = np.concatenate([np.asarray(x, np.int32) for x in forced_dur]).astype(np.int32, copy=False)
             if forced.shape[0] != R:
                 raise ValueError("forced_dur must give one duration per token")
-        _lib.check(self._lib.ttsb_synthesize_begin(self._h, _ptr(ids), _ptr(tok_off), B, _ptr(ref), _ptr(sp), int(padded_lstm),
-                                                   _ptr(forced), _ptr(pred), _ptr(dur), _ptr(f_off)))
+        if by_voice:
+            _lib.check(self._lib.ttsb_synthesize_begin_voices(self._h, _ptr(ids), _ptr(tok_off), B, _ptr(vs), _ptr(vr), _ptr(sp), int(padded_lstm),
+                                                              _ptr(forced), _ptr(pred), _ptr(dur), _ptr(f_off)))
+        else:
+            _lib.check(self._lib.ttsb_synthesize_begin(self._h, _ptr(ids), _ptr(tok_off), B, _ptr(ref), _ptr(sp), int(padded_lstm),
+                                                       _ptr(forced), _ptr(pred), _ptr(dur), _ptr(f_off)))
         RF = int(f_off[-1])
         nz, nz_mem = None, _lib.MEM_HOST
         if noise is not None:

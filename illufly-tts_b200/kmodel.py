@@ -177,6 +177,57 @@ class BatchKModel:
             return [torch.zeros(SILENCE_SAMPLES) for _ in range(B)]
 
 
+    # ---- voice packs resident on the device (the reference: pipeline.py:78-109 cache, :596-603 row select) ----
+    def register_voice(self, voice_id: str, pack: torch.Tensor) -> int:
+        """Upload ``pack`` ([510,1,256]: ``pipeline.voices[voice_id]``) to the engine once; returns its slot.  Registering the same id
+        again with the same tensor object is a no-op, with another tensor it replaces the pack."""
+        reg = self.__dict__.setdefault("_voice_slots", {})
+        ent = reg.get(voice_id)
+        if ent is not None and ent[1] is pack:
+            return ent[0]
+        slot = ent[0] if ent is not None else len(reg)
+        rows = self.engine.set_voice_pack(slot, pack)
+        reg[voice_id] = (slot, pack, rows)
+        return slot
+
+    @torch.no_grad()
+    def forward_batch_voices(self, phonemes_batch: Sequence[str], voice_ids: Sequence[str], speeds: Optional[Sequence[float]] = None, *,
+                             noise=None, seed: int = 0):
+        """``forward_batch`` with the style rows taken from registered voice packs on the device: utterance b uses row
+        ``len(phonemes_batch[b]) - 1`` of ``voice_ids[b]``'s pack (pipeline.py:596-601), clamped to the pack.  Same results, bit for bit,
+        as ``forward_batch`` with ``torch.stack([pack[len(ps) - 1] ...])``; no style bytes cross PCIe per batch.  Error surface of
+        ``forward_batch`` (kmodel.py:27-30, 147-150)."""
+        if speeds is None:
+            speeds = [1.0] * len(phonemes_batch)
+        for i, ph in enumerate(phonemes_batch):
+            if not ph or len(ph) < 5:
+                logger.error("phoneme sequence #%d is empty or too short: %r", i, ph)
+                if self.strict:
+                    raise ValueError(f"phoneme sequence #{i} is empty or too short")
+                return [torch.zeros(SILENCE_SAMPLES)]
+        B = len(phonemes_batch)
+        try:
+            reg = self.__dict__.get("_voice_slots", {})
+            slots, rows = [], []
+            for ph, vid in zip(phonemes_batch, voice_ids):
+                if vid not in reg:
+                    raise KeyError(f"voice {vid!r} is not registered (register_voice)")
+                slot, _, nrows = reg[vid]
+                slots.append(slot)
+                rows.append(min(max(len(ph), 1) - 1, nrows - 1))
+            ids_list = [phonemes_to_ids(self.vocab, ph) for ph in phonemes_batch]
+            if self.ragged_silence and len({len(x) for x in ids_list}) > 1:
+                raise RuntimeError("ragged batch (reference kmodel.py:132 raises on it)")
+            res = self.engine.synthesize(ids_list, None, [float(s) for s in speeds], noise=noise, seed=seed, padded_lstm=self.padded_lstm,
+                                         voice_slots=slots, voice_rows=rows)
+            return res.audio
+        except Exception as exc:
+            if self.strict:
+                raise
+            logger.error("batched synthesis failed: %s", exc, exc_info=True)
+            return [torch.zeros(SILENCE_SAMPLES) for _ in range(B)]
+
+
 def install_into_reference():
     """Make ``illufly_tts.core.kmodel.BatchKModel`` resolve to this class, so the unmodified reference pipeline
     (core/pipeline.py:19 ``from .kmodel import BatchKModel``) constructs the B200 engine.  The reference tree is not

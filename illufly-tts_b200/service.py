@@ -108,6 +108,9 @@ class TTSServiceManager:
         self.output_dir = output_dir
         self.model = model
         self.voices = voices
+        # voice packs resident on the device when the model offers it (BatchKModel on a B200); a stand-in model gets stacked rows
+        self._resident = callable(getattr(model, "register_voice", None)) and callable(getattr(model, "forward_batch_voices", None))
+        self._resident_ids: Dict[str, Any] = {}
         self.token_budget = token_budget
         self.max_batch_items = max_batch_items
         self.max_wait_time = max_wait_time
@@ -296,10 +299,16 @@ class TTSServiceManager:
         return len(dead)
 
     def _run(self, units: List[tuple]) -> List[torch.Tensor]:
-        """One engine call for ``units`` = [(phonemes, style row [1,256], speed)].  Worker thread."""
+        """One engine call for ``units`` = [(phonemes, style row [1,256], speed[, voice id])].  Worker thread.
+        A model with resident voice packs (``BatchKModel.register_voice`` / ``forward_batch_voices``) gets voice ids:
+        the packs were uploaded once and the rows are picked on the device; any other model gets the stacked rows as the reference's
+        does (pipeline.py:603)."""
         ph = [u[0] for u in units]
-        ref = torch.stack([u[1] for u in units])           # [B,1,256] like pipeline.py:603
-        out = self.model.forward_batch(ph, ref, [u[2] for u in units])
+        if self._resident and all(len(u) > 3 and u[3] in self._resident_ids for u in units):
+            out = self.model.forward_batch_voices(ph, [u[3] for u in units], [u[2] for u in units])
+        else:
+            ref = torch.stack([u[1] for u in units])       # [B,1,256] like pipeline.py:603
+            out = self.model.forward_batch(ph, ref, [u[2] for u in units])
         if len(out) != len(units):
             raise RuntimeError(f"model returned {len(out)} waveforms for {len(units)} utterances")
         return list(out)
@@ -339,7 +348,10 @@ class TTSServiceManager:
                 t.started_at = now
                 try:
                     pack = self.voices[t.voice_id]
-                    mine = [(c, voice_row(pack, len(c)), float(t.speed)) for c in t.chunks]
+                    if self._resident and self._resident_ids.get(t.voice_id) is not pack:
+                        await asyncio.to_thread(self.model.register_voice, t.voice_id, pack)      # once per voice (again if the pack object changes)
+                        self._resident_ids[t.voice_id] = pack
+                    mine = [(c, voice_row(pack, len(c)), float(t.speed), t.voice_id) for c in t.chunks]
                 except Exception as exc:
                     t.status, t.error, t.completed_at = TaskStatus.FAILED, f"could not assemble the request: {exc!r}", time.time()
                     continue

@@ -136,6 +136,21 @@ TTSB_API int ttsb_synthesize_begin(ttsb_engine* e, const int32_t* ids, const int
                           const float* speeds, int padded_lstm, const int32_t* forced_dur, int32_t* pred_dur, float* duration,
                           int32_t* frame_offsets);
 
+/* Voice packs resident on the device.  The reference keeps every loaded voice pack ([510,1,256] fp32) in a host
+ * dict (core/pipeline.py:78-109 load_voice) and, per request, picks the row for the utterance's phoneme count and stacks the rows of a
+ * batch into ref_s (pipeline.py:596-603) - one host gather + one host->device copy per batch.  Here a pack is uploaded once into a
+ * slot; begin_voices() takes (slot, row) per utterance and gathers the style rows on the device.
+ *   voice_pack_set: pack = host fp32 [rows,256] (the pack with its singleton dimension squeezed), copied; an existing pack in the slot
+ *                   is replaced; pack == NULL empties the slot.  slot in [0, 4096).  Not to be called between begin() and finish().
+ *   begin_voices:   as ttsb_synthesize_begin with voice_slot / voice_row (host int32 [B]) in place of ref_s; row = the index the
+ *                   reference uses, len(phonemes) - 1, clamped by the caller to the pack (pipeline.py:599-601).  Results are
+ *                   bit-identical to begin() with the same rows passed as ref_s.
+ */
+TTSB_API int ttsb_engine_voice_pack_set(ttsb_engine* e, int slot, const float* pack, int rows);
+TTSB_API int ttsb_synthesize_begin_voices(ttsb_engine* e, const int32_t* ids, const int32_t* token_offsets, int B, const int32_t* voice_slot,
+                                 const int32_t* voice_row, const float* speeds, int padded_lstm, const int32_t* forced_dur,
+                                 int32_t* pred_dur, float* duration, int32_t* frame_offsets);
+
 /* finish(): kmodel.py:120-143 — length regulation, F0Ntrain, text_encoder, decoder + iSTFTNet generator.
  *   noise       fp32 [600*sum F, 9] N(0,1) samples for SineGen (injected for parity), in `noise_mem`; or NULL:
  *               the engine draws them in-kernel (Philox).  The stream of an utterance is keyed by (`seed`, a hash of that

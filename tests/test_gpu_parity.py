@@ -567,3 +567,35 @@ def test_two_conv_kernels_agree_on_the_generator(tmp_path):
         assert a.shape == m.shape
         snr = snr_db(m, a)
         assert snr >= 55.0, f"utterance {b}: the two conv kernels differ, SNR {snr:.1f} dB"
+
+
+def test_resident_voice_packs_give_the_same_bits(checkpoint):
+    """SURVEY 8(f) row 3 on the engine: voice packs uploaded once (ttsb_engine_voice_pack_set), style rows picked on the device by
+    (slot, row) (ttsb_synthesize_begin_voices) - the waveforms are the bits of forward_batch with the rows stacked on the host as
+    pipeline.py:596-603 does; a voice that was never registered, a slot without a pack and a row outside the pack are refused."""
+    model = pkg.BatchKModel(config=synthetic_config(), model=checkpoint, precision=pkg.PRECISION_FP16, strict=True, padded_lstm=False).to("cuda:0")
+    packs = {"a": synthetic_voice_pack(1), "b": synthetic_voice_pack(2)}
+    g = torch.Generator().manual_seed(33)
+    phon = [ids_to_phonemes(random_ids(g, n)) for n in (12, 47, 80, 5, 33)]
+    voices = ["a", "b", "b", "a", "b"]
+    for vid, p in packs.items():
+        model.register_voice(vid, p)
+    assert model.register_voice("a", packs["a"]) == 0                  # same object: no second upload, same slot
+    from illufly_tts_b200.service import voice_row
+    ref = torch.stack([voice_row(packs[v], len(p)) for p, v in zip(phon, voices)])
+    want = model.forward_batch(phon, ref, [1.0, 0.9, 1.1, 1.0, 1.2], seed=5)
+    got = model.forward_batch_voices(phon, voices, [1.0, 0.9, 1.1, 1.0, 1.2], seed=5)
+    assert len(got) == len(want) and all(torch.equal(x, y) for x, y in zip(got, want))
+    with pytest.raises(Exception):
+        model.forward_batch_voices(phon[:1], ["nobody"], [1.0])
+    eng = model.engine
+    ids = [[0] + random_ids(g, 10)[1:-1] + [0]]
+    with pytest.raises(Exception):
+        eng.synthesize(ids, None, [1.0], voice_slots=[7], voice_rows=[0])          # empty slot
+    with pytest.raises(Exception):
+        eng.synthesize(ids, None, [1.0], voice_slots=[0], voice_rows=[510])        # row outside the pack
+    eng.set_voice_pack(1, None)                                                    # emptied slot
+    with pytest.raises(Exception):
+        eng.synthesize(ids, None, [1.0], voice_slots=[1], voice_rows=[3])
+    r = eng.synthesize(ids, None, [1.0], voice_slots=[0], voice_rows=[9], seed=1)  # the engine still works after the refusals
+    assert r.audio[0].numel() == 600 * int(r.pred_dur[0].sum())

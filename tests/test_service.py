@@ -370,3 +370,43 @@ def test_service_audio_egress_and_reference_constructor(tmp_path, monkeypatch):
     import base64
     assert base64.b64decode(svc.task_wav_base64(tid))[:4] == b"RIFF"
     sys.modules.pop("illufly_tts.core.kmodel", None)
+
+
+class ResidentModel(FakeModel):
+    """a model with device-resident voice packs (BatchKModel.register_voice / forward_batch_voices): remembers what it was given"""
+
+    def __init__(self):
+        super().__init__()
+        self.registered, self.voice_calls = [], []
+        self.packs = {}
+
+    def register_voice(self, voice_id, pack):
+        self.registered.append(voice_id)
+        self.packs[voice_id] = pack
+        return len(self.packs) - 1
+
+    def forward_batch_voices(self, phonemes, voice_ids, speeds=None):
+        self.voice_calls.append((list(phonemes), list(voice_ids)))
+        rows = torch.stack([voice_row(self.packs[v], len(p)) for p, v in zip(phonemes, voice_ids)])
+        return [torch.full((600 * len(p),), float(len(p)) + float(rows[i, 0, 0]) * 1e-6) for i, p in enumerate(phonemes)]
+
+
+def test_resident_voice_packs_are_registered_once_and_selected_by_id():
+    """with a model that keeps voice packs on the device the service uploads a pack once per voice and then sends
+    voice ids, not stacked style rows (pipeline.py:596-603 stacks rows on the host for every batch); the waveforms equal what the
+    stacked-row path gives.  A stand-in model without the two methods keeps the reference's path (every other test of this file)."""
+    async def main(model):
+        svc = pkg.TTSServiceManager(model, dict(VOICES), token_budget=40)
+        await svc.start()
+        ids = [await svc.submit_task("abcdefgh" + "x" * k, "v1" if k % 2 else "v2", 1.0, user_id=f"u{k % 3}") for k in range(7)]
+        await drain(svc, ids)
+        out = [svc.tasks[i].audio_chunks[0] for i in ids]
+        await svc.stop()
+        return out
+    res, plain = ResidentModel(), FakeModel()
+    a = run(main(res))
+    b = run(main(plain))
+    assert sorted(res.registered) == ["v1", "v2"]                      # once per voice, not once per batch
+    assert res.voice_calls and not res.calls                           # only the resident entry point was used
+    assert all(set(v) <= {"v1", "v2"} for _, v in res.voice_calls)
+    assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
