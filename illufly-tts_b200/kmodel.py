@@ -118,6 +118,7 @@ class BatchKModel:
         if self._engine is not None:
             self._engine.close()
         self._engine = Engine(self._ckpt, dev, self.precision)
+        self.__dict__.pop("_voice_slots", None)          # voice packs live in the engine: a new engine starts with none
         self._device = self._engine.device
         return self
 
