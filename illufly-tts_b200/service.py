@@ -348,9 +348,12 @@ class TTSServiceManager:
                 t.started_at = now
                 try:
                     pack = self.voices[t.voice_id]
-                    if self._resident and self._resident_ids.get(t.voice_id) is not pack:
-                        await asyncio.to_thread(self.model.register_voice, t.voice_id, pack)      # once per voice (again if the pack object changes)
-                        self._resident_ids[t.voice_id] = pack
+                    if self._resident:
+                        if self._resident_ids.get(t.voice_id) is not pack:
+                            await asyncio.to_thread(self.model.register_voice, t.voice_id, pack)  # once per voice (again if the pack object changes)
+                            self._resident_ids[t.voice_id] = pack
+                        else:
+                            self.model.register_voice(t.voice_id, pack)    # a no-op, unless the model has been moved to a new engine since
                     mine = [(c, voice_row(pack, len(c)), float(t.speed), t.voice_id) for c in t.chunks]
                 except Exception as exc:
                     t.status, t.error, t.completed_at = TaskStatus.FAILED, f"could not assemble the request: {exc!r}", time.time()
